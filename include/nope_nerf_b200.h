@@ -1,0 +1,117 @@
+/* nope_nerf_b200 — C ABI of the B200-native NoPe-NeRF render / pose-optimisation hot path.
+ *
+ * The reference (ActiveVisionLab/nope-nerf @ 47c861f6) is pure Python/PyTorch and has no
+ * FFI layer; the drop-in boundary is its Python class surface.  The host
+ * mirror of that surface (nope_nerf_b200/model/) binds THIS library with ctypes; the
+ * reference-side stub a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless named host_*; fp32 contiguous;
+ * buffers are borrowed for the duration of the call; all work is enqueued on `stream`
+ * (a cudaStream_t passed as void*), nothing synchronises; return 0 = ok, negative = error
+ * (nnb_last_error() gives the message, thread-local).  No exceptions cross the ABI, no
+ * hidden allocations: scratch memory is a caller-provided workspace sized by
+ * nnb_workspace_bytes().
+ */
+#ifndef NOPE_NERF_B200_H
+#define NOPE_NERF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNB_NUM_PARAMS 595844 /* OfficialStaticNerf, hidden_dim 256 (model/official_nerf.py:20-37) */
+
+/* rendering flags (configs/default.yaml:32-44 -> model/rendering.py:41-46) */
+#define NNB_DIST_ALPHA 1u   /* rendering.dist_alpha     (rendering.py:122-128, official_nerf.py:82) */
+#define NNB_NDC 2u          /* rendering.sample_option == 'ndc' (rendering.py:168-180)           */
+#define NNB_NORMALISE 4u    /* rendering.normalise_ray  (rendering.py:68-71)                      */
+#define NNB_USE_DIR 8u      /* rendering.use_ray_dir    (rendering.py:103-104)                    */
+#define NNB_WHITE_BG 16u    /* rendering.white_background (rendering.py:145-147)                  */
+#define NNB_EVAL 32u        /* eval_ argument           (rendering.py:150-154)                    */
+#define NNB_SOFTPLUS 64u    /* model.occ_activation == 'softplus' (official_nerf.py:77-80)        */
+#define NNB_SHIFT_FIRST 128u /* training.shift_first    (training.py:241-245)                     */
+#define NNB_STASH 256u      /* keep activations in the workspace for nnb_render_bwd               */
+
+/* engines */
+#define NNB_ENGINE_SIMT 0 /* exact fp32 FMA path                                        */
+#define NNB_ENGINE_TC 1   /* tcgen05 tensor cores, split-fp16 (hi/lo) operands, fp32 acc */
+
+/* One ray batch of one camera.  Mirrors the arguments of nope_nerf.forward
+ * (model/network.py:19-20) + Renderer.nope_nerf (model/rendering.py:36-37) after the host
+ * mirror has resolved world_mat -> c2w (training.py:238 / common.py:139-141). */
+typedef struct nnb_render_args {
+  const float* weights;   /* [NNB_NUM_PARAMS] flat, OfficialStaticNerf.parameters() order           */
+  const float* c2w;       /* [16] row-major camera-to-world (LearnPose.forward, poses.py:23-31)     */
+  const float* cam;       /* [16] camera_mat diag(kx,ky,-1,1) (dataset.py:101-104); [0],[5] are read */
+  const int64_t* ray_idx; /* [N] row-major pixel ids (training.py:257) or NULL                      */
+  const float* pixels;    /* [N,2] in [-1,1] (common.py:13-39) or NULL -> derived from ray_idx,H,W  */
+  const float* depth;     /* [N] prior depth per ray, or NULL -> gathered from depth_map           */
+  const float* depth_map; /* [h_d,w_d] raw DPT map (network.py:22-24 nearest gather)                */
+  const float* scale;     /* [1] depth distortion scale or NULL (=1)  (distortions.py:19-27)        */
+  const float* shift;     /* [1] depth distortion shift or NULL (=0)                                */
+  const float* noise;     /* [N,S] stratified jitter U[0,1) (rendering.py:189) or NULL              */
+  int32_t N, S, H, W, h_d, w_d;
+  float near_, far_;      /* rendering.depth_range                                                  */
+  uint32_t flags;
+  int32_t engine;
+  /* outputs (rendering.py:159-166; depth_* are dense, `mask` selects the reference's rows) */
+  float* rgb;        /* [N,3] */
+  float* depth_pred; /* [N]   */
+  float* depth_gt;   /* [N]   */
+  uint8_t* mask;     /* [N]   */
+  float* z_vals;     /* [N,S] or NULL */
+  float* alpha;      /* [N,S] or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} nnb_render_args;
+
+typedef struct nnb_render_bwd_args {
+  nnb_render_args fwd;       /* same inputs / workspace as the forward call (NNB_STASH set)  */
+  const float* g_rgb;        /* [N,3] */
+  const float* g_depth_pred; /* [N] dense (0 where masked out) or NULL */
+  const float* g_depth_gt;   /* [N] dense or NULL                      */
+  /* outputs, all ACCUMULATED (+=): caller zeroes them */
+  float* g_weights; /* [NNB_NUM_PARAMS] or NULL (pose-only: Trainer_pose, eval_pose_one_epoch.py:25-41) */
+  float* g_c2w;     /* [16] (rows 0..2 written) */
+  float* g_cam;     /* [16] ([0],[5] written) or NULL */
+  float* g_depth;   /* [N] d/d prior depth (overwritten) or NULL */
+  float* g_scale_shift; /* [2] d/d scale, d/d shift when depth_map is used, or NULL */
+} nnb_render_bwd_args;
+
+const char* nnb_last_error(void);
+int nnb_version(void);
+/* bytes of workspace needed by nnb_render_fwd (+bwd when NNB_STASH) */
+size_t nnb_workspace_bytes(int32_t N, int32_t S, uint32_t flags, int32_t engine);
+int nnb_render_fwd(const nnb_render_args* a, void* stream);
+int nnb_render_bwd(const nnb_render_bwd_args* a, void* stream);
+
+/* LearnPose.forward (model/poses.py:23-31): c2w = [Exp(r[id]) t[id]; 0 1] @ init_c2w[id] */
+int nnb_pose_fwd(const float* r, const float* t, const float* init_c2w /*[V,16] or NULL*/, int32_t cam_id,
+                 float* c2w /*[16]*/, void* stream);
+/* adjoint: g_r[cam_id], g_t[cam_id] += ... ; g_r/g_t are [V,3] (either may be NULL) */
+int nnb_pose_bwd(const float* r, const float* t, const float* init_c2w, int32_t cam_id, const float* g_c2w,
+                 float* g_r, float* g_t, void* stream);
+
+/* Loss.forward photometric + depth-L1 terms (model/losses.py:27-32,59-61,192,196-202) fused with
+ * the cotangent seeds of nnb_render_bwd.  rgb_gt is either explicit [N,3] or gathered from a planar
+ * image [3,H*W] at ray_idx (training.py:258-259).  out_losses = {loss, loss_rgb, loss_depth, l2_mean}. */
+int nnb_loss_rgb_depth(const float* rgb, const float* rgb_gt, const float* img, const int64_t* ray_idx, int32_t HW,
+                       const float* depth_pred, const float* depth_gt, const uint8_t* mask, int32_t N,
+                       float w_rgb, float w_depth, int32_t rgb_l2, float grad_scale, float* out_losses /*[4]*/,
+                       float* g_rgb, float* g_depth_pred, float* g_depth_gt, void* stream);
+
+/* Loss.get_pc_loss 'dense' (model/losses.py:114-148): symmetric mean nearest-neighbour distance.
+ * X [P,3], Y [Q,3]; idx_xy [P], idx_yx [Q] int32 scratch; loss [1] (+=); optional adjoints (+=). */
+int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, int32_t* idx_xy, int32_t* idx_yx,
+                float* loss, float weight, float* gX, float* gY, void* stream);
+
+/* torch.optim.Adam step (train.py:58,99,117 defaults) over one flat buffer. step_count is the
+ * 1-based step; lr/betas/eps as torch. */
+int nnb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,
+                  float beta2, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

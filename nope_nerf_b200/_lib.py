@@ -1,0 +1,70 @@
+"""ctypes binding of libnope_nerf_b200.so (include/nope_nerf_b200.h).
+
+The product path has NO CPU fallback: importing this module loads the CUDA library and
+raises immediately if it is missing; every call raises RuntimeError with nnb_last_error()
+on a non-zero return code."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnope_nerf_b200.so")
+
+NUM_PARAMS = 595844
+DIST_ALPHA, NDC, NORMALISE, USE_DIR, WHITE_BG, EVAL, SOFTPLUS, SHIFT_FIRST, STASH = 1, 2, 4, 8, 16, 32, 64, 128, 256
+ENGINE_SIMT, ENGINE_TC = 0, 1
+
+_f = C.c_void_p  # device pointers travel as integers
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [("weights", _f), ("c2w", _f), ("cam", _f), ("ray_idx", _f), ("pixels", _f), ("depth", _f),
+                ("depth_map", _f), ("scale", _f), ("shift", _f), ("noise", _f),
+                ("N", C.c_int32), ("S", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("h_d", C.c_int32), ("w_d", C.c_int32),
+                ("near_", C.c_float), ("far_", C.c_float), ("flags", C.c_uint32), ("engine", C.c_int32),
+                ("rgb", _f), ("depth_pred", _f), ("depth_gt", _f), ("mask", _f), ("z_vals", _f), ("alpha", _f),
+                ("workspace", _f), ("workspace_bytes", C.c_size_t)]
+
+
+class RenderBwdArgs(C.Structure):
+    _fields_ = [("fwd", RenderArgs), ("g_rgb", _f), ("g_depth_pred", _f), ("g_depth_gt", _f),
+                ("g_weights", _f), ("g_c2w", _f), ("g_cam", _f), ("g_depth", _f), ("g_scale_shift", _f)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "nope_nerf_b200: CUDA library %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.nnb_last_error.restype = C.c_char_p
+    lib.nnb_version.restype = C.c_int
+    lib.nnb_workspace_bytes.restype = C.c_size_t
+    lib.nnb_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_uint32, C.c_int32]
+    lib.nnb_render_fwd.argtypes = [C.POINTER(RenderArgs), C.c_void_p]
+    lib.nnb_render_bwd.argtypes = [C.POINTER(RenderBwdArgs), C.c_void_p]
+    lib.nnb_pose_fwd.argtypes = [_f, _f, _f, C.c_int32, _f, C.c_void_p]
+    lib.nnb_pose_bwd.argtypes = [_f, _f, _f, C.c_int32, _f, _f, _f, C.c_void_p]
+    lib.nnb_loss_rgb_depth.argtypes = [_f, _f, _f, _f, C.c_int32, _f, _f, _f, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                       C.c_float, _f, _f, _f, _f, C.c_void_p]
+    lib.nnb_chamfer.argtypes = [_f, C.c_int32, _f, C.c_int32, _f, _f, _f, C.c_float, _f, _f, C.c_void_p]
+    lib.nnb_adam_step.argtypes = [_f, _f, _f, _f, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    for name in ("nnb_refstage_fwd", "nnb_refstage_bwd"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = C.c_int
+    return lib
+
+
+lib = _load()
+
+EXPORTS = ["nnb_last_error", "nnb_version", "nnb_workspace_bytes", "nnb_render_fwd", "nnb_render_bwd", "nnb_pose_fwd",
+           "nnb_pose_bwd", "nnb_loss_rgb_depth", "nnb_chamfer", "nnb_adam_step"]
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib.nnb_last_error().decode()))
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else t.data_ptr()

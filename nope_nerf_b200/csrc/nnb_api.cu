@@ -1,0 +1,128 @@
+// extern "C" boundary (include/nope_nerf_b200.h): argument validation, workspace carving,
+// engine dispatch.  No torch types, no allocation, no synchronisation.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include "nnb_workspace.cuh"
+
+cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st);
+cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
+#ifdef NNB_WITH_TC
+cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st);
+cudaError_t tc_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
+size_t tc_workspace_extra(int N, int S, uint32_t flags);
+#endif
+cudaError_t launch_pose_fwd(const float*, const float*, const float*, int, float*, cudaStream_t);
+cudaError_t launch_pose_bwd(const float*, const float*, const float*, int, const float*, float*, float*, cudaStream_t);
+cudaError_t launch_loss(const float*, const float*, const float*, const int64_t*, int, const float*, const float*, const uint8_t*,
+                        int, float, float, int, float, float*, float*, float*, float*, cudaStream_t);
+cudaError_t launch_chamfer(const float*, int, const float*, int, int*, int*, float*, float, float*, float*, cudaStream_t);
+cudaError_t launch_adam(float*, const float*, float*, float*, int64_t, int, float, float, float, float, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  return fail(-100 - (int)e, "%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));
+}
+
+extern "C" {
+
+const char* nnb_last_error(void) { return g_err; }
+int nnb_version(void) { return 100; }
+
+size_t nnb_workspace_bytes(int32_t N, int32_t S, uint32_t flags, int32_t engine) {
+  if (N <= 0 || S <= 0) return 0;
+  WsLayout L = make_layout(N, S, flags, engine);
+  size_t tot = L.total;
+#ifdef NNB_WITH_TC
+  if (engine == NNB_ENGINE_TC) tot += tc_workspace_extra(N, S, flags);
+#endif
+  return tot;
+}
+
+static int check_args(const nnb_render_args* a) {
+  if (!a) return fail(-1, "null args");
+  if (a->N <= 0) return fail(-2, "N must be positive (got %d)", a->N);
+  if (a->S < 2 || a->S > 256) return fail(-2, "S must be in [2,256] (got %d)", a->S);
+  if (!a->weights || !a->c2w || !a->cam) return fail(-3, "weights / c2w / cam must be non-null");
+  if (!a->ray_idx && !a->pixels) return fail(-3, "need ray_idx or pixels");
+  if (!a->pixels && (a->H < 2 || a->W < 2)) return fail(-3, "H,W needed to derive pixels from ray_idx");
+  if (!a->depth && !(a->depth_map && a->ray_idx && a->h_d > 0 && a->w_d > 0 && a->H > 0 && a->W > 0))
+    return fail(-3, "need depth[N] or (depth_map,h_d,w_d,H,W,ray_idx)");
+  if (!a->rgb || !a->depth_pred || !a->depth_gt || !a->mask) return fail(-3, "output pointers must be non-null");
+  if (a->engine != NNB_ENGINE_SIMT && a->engine != NNB_ENGINE_TC) return fail(-4, "unknown engine %d", a->engine);
+#ifndef NNB_WITH_TC
+  if (a->engine == NNB_ENGINE_TC) return fail(-4, "library built without the tcgen05 engine");
+#endif
+  size_t need = nnb_workspace_bytes(a->N, a->S, a->flags, a->engine);
+  if (!a->workspace || a->workspace_bytes < need)
+    return fail(-5, "workspace too small: have %zu need %zu", a->workspace_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(a->workspace) & 255) != 0) return fail(-5, "workspace must be 256-byte aligned");
+  return 0;
+}
+
+int nnb_render_fwd(const nnb_render_args* a, void* stream) {
+  int rc = check_args(a); if (rc) return rc;
+  WsLayout L = make_layout(a->N, a->S, a->flags, a->engine);
+  cudaError_t e;
+#ifdef NNB_WITH_TC
+  if (a->engine == NNB_ENGINE_TC) e = tc_render_fwd(*a, L, (cudaStream_t)stream); else
+#endif
+  e = simt_render_fwd(*a, L, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_render_fwd");
+}
+
+int nnb_render_bwd(const nnb_render_bwd_args* b, void* stream) {
+  if (!b) return fail(-1, "null args");
+  int rc = check_args(&b->fwd); if (rc) return rc;
+  if (!(b->fwd.flags & NNB_STASH)) return fail(-6, "nnb_render_bwd needs the forward call to have run with NNB_STASH");
+  if (!b->g_rgb || !b->g_c2w) return fail(-3, "g_rgb and g_c2w must be non-null");
+  WsLayout L = make_layout(b->fwd.N, b->fwd.S, b->fwd.flags, b->fwd.engine);
+  cudaError_t e;
+#ifdef NNB_WITH_TC
+  if (b->fwd.engine == NNB_ENGINE_TC) e = tc_render_bwd(*b, L, (cudaStream_t)stream); else
+#endif
+  e = simt_render_bwd(*b, L, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_render_bwd");
+}
+
+int nnb_pose_fwd(const float* r, const float* t, const float* init, int32_t cam, float* c2w, void* stream) {
+  if (!r || !t || !c2w || cam < 0) return fail(-3, "nnb_pose_fwd: bad arguments");
+  cudaError_t e = launch_pose_fwd(r, t, init, cam, c2w, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_pose_fwd");
+}
+int nnb_pose_bwd(const float* r, const float* t, const float* init, int32_t cam, const float* g, float* gr, float* gt, void* stream) {
+  if (!r || !t || !g || cam < 0) return fail(-3, "nnb_pose_bwd: bad arguments");
+  cudaError_t e = launch_pose_bwd(r, t, init, cam, g, gr, gt, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_pose_bwd");
+}
+
+int nnb_loss_rgb_depth(const float* rgb, const float* rgb_gt, const float* img, const int64_t* ray_idx, int32_t HW,
+                       const float* dp, const float* dg, const uint8_t* mask, int32_t N, float w_rgb, float w_depth,
+                       int32_t rgb_l2, float grad_scale, float* out, float* g_rgb, float* g_dp, float* g_dg, void* stream) {
+  if (!rgb || !(rgb_gt || (img && ray_idx)) || !dp || !dg || !mask || !out || !g_rgb || !g_dp || !g_dg || N <= 0)
+    return fail(-3, "nnb_loss_rgb_depth: bad arguments");
+  cudaError_t e = launch_loss(rgb, rgb_gt, img, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, rgb_l2, grad_scale, out, g_rgb, g_dp, g_dg,
+                              (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_loss_rgb_depth");
+}
+
+int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, int32_t* ixy, int32_t* iyx, float* loss, float weight,
+                float* gX, float* gY, void* stream) {
+  if (!X || !Y || !ixy || !iyx || !loss || P <= 0 || Q <= 0 || ((gX == nullptr) != (gY == nullptr)))
+    return fail(-3, "nnb_chamfer: bad arguments");
+  cudaError_t e = launch_chamfer(X, P, Y, Q, ixy, iyx, loss, weight, gX, gY, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_chamfer");
+}
+
+int nnb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float b1, float b2, float eps,
+                  void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || step < 1) return fail(-3, "nnb_adam_step: bad arguments");
+  cudaError_t e = launch_adam(p, g, m, v, n, step, lr, b1, b2, eps, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_adam_step");
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// Small kernels around the render path: SE(3) exp-map pose (forward + adjoint), fused
+// photometric/depth loss + cotangent seeds, dense chamfer point-cloud loss, Adam.
+#include "nnb_common.cuh"
+
+namespace {
+
+// ---- LearnPose.forward (model/poses.py:23-31, model/common.py:277-330) ----------------
+__device__ void exp_so3(const float r[3], float R[9], float* n_out, float* A_out, float* B_out) {
+  float n0 = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  float n = n0 + 1e-15f;                                   // common.py:296
+  float A = sinf(n) / n, B = (1.f - cosf(n)) / (n * n);
+  float K[9] = {0.f, -r[2], r[1], r[2], 0.f, -r[0], -r[1], r[0], 0.f};
+  float K2[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    float s = 0.f; for (int k = 0; k < 3; ++k) s += K[3 * i + k] * K[3 * k + j];
+    K2[3 * i + j] = s;
+  }
+  for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.f : 0.f) + A * K[i] + B * K2[i];
+  *n_out = n0; *A_out = A; *B_out = B;
+}
+
+__global__ void pose_fwd_k(const float* r, const float* t, const float* init, int cam, float* c2w) {
+  if (threadIdx.x != 0) return;
+  float rv[3] = {r[3 * cam], r[3 * cam + 1], r[3 * cam + 2]}, R[9], n0, A, B;
+  exp_so3(rv, R, &n0, &A, &B);
+  float c[16] = {R[0], R[1], R[2], t[3 * cam], R[3], R[4], R[5], t[3 * cam + 1], R[6], R[7], R[8], t[3 * cam + 2], 0, 0, 0, 1};
+  if (init) {
+    const float* I = init + 16 * cam;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+      float s = 0.f; for (int k = 0; k < 4; ++k) s += c[4 * i + k] * I[4 * k + j];
+      c2w[4 * i + j] = s;
+    }
+  } else for (int i = 0; i < 16; ++i) c2w[i] = c[i];
+}
+
+__global__ void pose_bwd_k(const float* r, const float* t, const float* init, int cam, const float* g_c2w, float* g_r, float* g_t) {
+  if (threadIdx.x != 0) return;
+  float g[16];
+  if (init) {  // c2w = C @ I  ->  gC = g @ I^T
+    const float* I = init + 16 * cam;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+      float s = 0.f; for (int k = 0; k < 4; ++k) s += g_c2w[4 * i + k] * I[4 * j + k];
+      g[4 * i + j] = s;
+    }
+  } else for (int i = 0; i < 16; ++i) g[i] = g_c2w[i];
+  if (g_t) for (int i = 0; i < 3; ++i) g_t[3 * cam + i] += g[4 * i + 3];
+  if (!g_r) return;
+  float rv[3] = {r[3 * cam], r[3 * cam + 1], r[3 * cam + 2]}, R[9], n0, A, B;
+  exp_so3(rv, R, &n0, &A, &B);
+  float gR[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) gR[3 * i + j] = g[4 * i + j];
+  float K[9] = {0.f, -rv[2], rv[1], rv[2], 0.f, -rv[0], -rv[1], rv[0], 0.f};
+  float K2[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { float s = 0.f; for (int k = 0; k < 3; ++k) s += K[3 * i + k] * K[3 * k + j]; K2[3 * i + j] = s; }
+  float gA = 0.f, gB = 0.f;
+  for (int i = 0; i < 9; ++i) { gA += gR[i] * K[i]; gB += gR[i] * K2[i]; }
+  // gK = A gR + B (gR K^T + K^T gR)
+  float gK[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < 3; ++k) { s1 += gR[3 * i + k] * K[3 * j + k]; s2 += K[3 * k + i] * gR[3 * k + j]; }
+    gK[3 * i + j] = A * gR[3 * i + j] + B * (s1 + s2);
+  }
+  float gr[3] = {gK[7] - gK[5], gK[2] - gK[6], gK[3] - gK[1]};
+  if (n0 > 0.f) {  // autograd's norm sub-gradient at r = 0 is 0
+    float n = n0 + 1e-15f;
+    float dA = (cosf(n) * n - sinf(n)) / (n * n);
+    float dB = (sinf(n) * n * n - (1.f - cosf(n)) * 2.f * n) / (n * n * n * n);
+    float gn = gA * dA + gB * dB;
+    for (int i = 0; i < 3; ++i) gr[i] += gn * rv[i] / n0;
+  }
+  for (int i = 0; i < 3; ++i) g_r[3 * cam + i] += gr[i];
+}
+
+// ---- Loss.forward rgb + depth terms (model/losses.py:27-32,59-61,192-202) --------------
+__device__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) sh[32] = t;
+  __syncthreads();
+  return sh[32];
+}
+
+__global__ void loss_rgb_depth_k(const float* rgb, const float* rgb_gt, const float* img, const int64_t* ray_idx, int HW,
+                                 const float* dp, const float* dg, const uint8_t* mask, int N, float w_rgb, float w_depth,
+                                 int rgb_l2, float grad_scale, float* out, float* g_rgb, float* g_dp, float* g_dg) {
+  __shared__ float sh[33];
+  float l1 = 0.f, l2 = 0.f, ld = 0.f, cnt = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    for (int c = 0; c < 3; ++c) {
+      float gt = rgb_gt ? rgb_gt[3 * n + c] : img[(size_t)c * HW + ray_idx[n]];
+      float d = rgb[3 * n + c] - gt;
+      l1 += fabsf(d); l2 += d * d;
+    }
+    if (mask[n]) { cnt += 1.f; ld += fabsf(dp[n] - dg[n]); }
+  }
+  l1 = block_sum(l1, sh); l2 = block_sum(l2, sh); ld = block_sum(ld, sh); cnt = block_sum(cnt, sh);
+  float cden = fmaxf(cnt, 1.f);
+  if (threadIdx.x == 0) {
+    float lrgb = (rgb_l2 ? l2 : l1) / (float)N, ldep = ld / cden;
+    out[0] = w_rgb * lrgb + w_depth * ldep; out[1] = lrgb; out[2] = ldep; out[3] = l2 / (3.f * (float)N);
+  }
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    for (int c = 0; c < 3; ++c) {
+      float gt = rgb_gt ? rgb_gt[3 * n + c] : img[(size_t)c * HW + ray_idx[n]];
+      float d = rgb[3 * n + c] - gt;
+      float g = rgb_l2 ? 2.f * d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      g_rgb[3 * n + c] = grad_scale * w_rgb * g / (float)N;
+    }
+    float gd = 0.f;
+    if (mask[n]) { float d = dp[n] - dg[n]; gd = grad_scale * w_depth * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / cden; }
+    g_dp[n] = gd; g_dg[n] = -gd;
+  }
+}
+
+// ---- dense chamfer (model/losses.py:114-148) ---------------------------------------------
+// nearest neighbour of every a in A among B (ties -> first index), then mean |a - b_nn| and adjoints
+__global__ void nn_search_k(const float* A, int P, const float* B, int Q, int* idx) {
+  __shared__ float sb[256 * 3];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  if (i < P) { ax = A[3 * i]; ay = A[3 * i + 1]; az = A[3 * i + 2]; }
+  float best = INFINITY; int bi = 0;
+  for (int q0 = 0; q0 < Q; q0 += 256) {
+    int nq = min(256, Q - q0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nq * 3; k += blockDim.x) sb[k] = B[3 * q0 + k];
+    __syncthreads();
+    for (int q = 0; q < nq; ++q) {
+      float dx = __fsub_rn(ax, sb[3 * q]), dy = __fsub_rn(ay, sb[3 * q + 1]), dz = __fsub_rn(az, sb[3 * q + 2]);
+      float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      if (d < best) { best = d; bi = q0 + q; }
+    }
+  }
+  if (i < P) idx[i] = bi;
+}
+__global__ void chamfer_acc_k(const float* A, int P, const float* B, const int* idx, float weight, float* loss, float* gA, float* gB) {
+  __shared__ float sh[33];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float dist = 0.f;
+  if (i < P) {
+    int j = idx[i];
+    float vx = A[3 * i] - B[3 * j], vy = A[3 * i + 1] - B[3 * j + 1], vz = A[3 * i + 2] - B[3 * j + 2];
+    dist = sqrtf(vx * vx + vy * vy + vz * vz);
+    if (gA && dist > 0.f) {
+      float s = weight / (dist * (float)P);
+      atomicAdd(gA + 3 * i, s * vx); atomicAdd(gA + 3 * i + 1, s * vy); atomicAdd(gA + 3 * i + 2, s * vz);
+      atomicAdd(gB + 3 * j, -s * vx); atomicAdd(gB + 3 * j + 1, -s * vy); atomicAdd(gB + 3 * j + 2, -s * vz);
+    }
+  }
+  float tot = block_sum(dist, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, tot / (float)P);
+}
+
+__global__ void adam_k(float* p, const float* g, float* m, float* v, int64_t n, float lr_bc1, float rsqrt_bc2, float b1, float b2, float eps) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  float mi = b1 * m[i] + (1.f - b1) * gi;
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] -= lr_bc1 * mi / (sqrtf(vi) * rsqrt_bc2 + eps);
+}
+
+}  // namespace
+
+cudaError_t launch_pose_fwd(const float* r, const float* t, const float* init, int cam, float* c2w, cudaStream_t st) {
+  pose_fwd_k<<<1, 32, 0, st>>>(r, t, init, cam, c2w); return cudaGetLastError();
+}
+cudaError_t launch_pose_bwd(const float* r, const float* t, const float* init, int cam, const float* g, float* gr, float* gt, cudaStream_t st) {
+  pose_bwd_k<<<1, 32, 0, st>>>(r, t, init, cam, g, gr, gt); return cudaGetLastError();
+}
+cudaError_t launch_loss(const float* rgb, const float* rgb_gt, const float* img, const int64_t* ray_idx, int HW, const float* dp,
+                        const float* dg, const uint8_t* mask, int N, float w_rgb, float w_depth, int l2, float gscale, float* out,
+                        float* g_rgb, float* g_dp, float* g_dg, cudaStream_t st) {
+  loss_rgb_depth_k<<<1, 1024, 0, st>>>(rgb, rgb_gt, img, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, l2, gscale, out, g_rgb, g_dp, g_dg);
+  return cudaGetLastError();
+}
+cudaError_t launch_chamfer(const float* X, int P, const float* Y, int Q, int* ixy, int* iyx, float* loss, float weight, float* gX,
+                           float* gY, cudaStream_t st) {
+  nn_search_k<<<(P + 255) / 256, 256, 0, st>>>(X, P, Y, Q, ixy);
+  nn_search_k<<<(Q + 255) / 256, 256, 0, st>>>(Y, Q, X, P, iyx);
+  chamfer_acc_k<<<(P + 255) / 256, 256, 0, st>>>(X, P, Y, ixy, weight, loss, gX, gY);
+  chamfer_acc_k<<<(Q + 255) / 256, 256, 0, st>>>(Y, Q, X, iyx, weight, loss, gY, gX);
+  return cudaGetLastError();
+}
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2, float eps, cudaStream_t st) {
+  double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  adam_k<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps);
+  return cudaGetLastError();
+}

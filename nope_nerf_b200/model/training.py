@@ -1,0 +1,371 @@
+"""Trainer (reference: model/training.py:14-379) — one optimisation step of NoPe-NeRF.
+
+Same constructor / train_step / render_visdata surface and the same loss_dict keys, but the
+render + photometric/depth loss + backward of a step are a fixed sequence of calls into the
+CUDA library (no autograd graph over the field):
+
+    nnb_pose_fwd -> nnb_render_fwd(STASH) -> nnb_loss_rgb_depth -> nnb_render_bwd -> nnb_pose_bwd
+
+Gradients land in ONE flat fp32 buffer [MLP | r | t | scales | shifts | 4 loss scalars] whose
+slices are installed as every parameter's .grad, so (a) train.py's own torch.optim.Adam
+instances step unchanged and (b) data-parallel training is a single NCCL all-reduce of that
+buffer per step.  The point-cloud / warped-RGB terms of the reference-image
+stage (training.py:280-365) run as torch ops + nnb_chamfer and accumulate into the same buffer.
+"""
+import logging
+import os
+import numpy as np
+import torch
+from torch.nn import functional as F
+from .. import ops
+from .. import _lib as L
+from .losses import Loss
+from .common import arange_pixels
+
+logger_py = logging.getLogger(__name__)
+
+
+def _host_diag_check(camera_mat):
+    """camera_mat must be diag(kx, ky, -1, 1) (dataset.py:101-104); checked on host tensors only."""
+    if camera_mat.is_cuda:
+        return
+    m = camera_mat.reshape(4, 4)
+    off = m - torch.diag(torch.diagonal(m))
+    if off.abs().max() != 0 or m[2, 2] != -1 or m[3, 3] != 1:
+        raise NotImplementedError("camera_mat must be diag(kx, ky, -1, 1)")
+
+
+class Trainer(object):
+    def __init__(self, model, optimizer, cfg, device=None, optimizer_pose=None, pose_param_net=None,
+                 optimizer_focal=None, focal_net=None, optimizer_distortion=None, distortion_net=None, **kwargs):
+        self.model = model
+        self.optimizer = optimizer
+        self.device = device
+        self.optimizer_pose = optimizer_pose
+        self.pose_param_net = pose_param_net
+        self.focal_net = focal_net
+        self.optimizer_focal = optimizer_focal
+        self.distortion_net = distortion_net
+        self.optimizer_distortion = optimizer_distortion
+        self.n_training_points = cfg['n_training_points']
+        self.rendering_technique = cfg['type']
+        self.vis_geo = cfg['vis_geo']
+        self.detach_gt_depth = cfg['detach_gt_depth']
+        self.pc_ratio = cfg['pc_ratio']
+        self.match_method = cfg['match_method']
+        self.shift_first = cfg['shift_first']
+        self.detach_ref_img = cfg['detach_ref_img']
+        self.scale_pcs = cfg['scale_pcs']
+        self.detach_rgbs_scale = cfg['detach_rgbs_scale']
+        self.vis_reprojection_every = cfg['vis_reprojection_every']
+        self.nearest_limit = cfg['nearest_limit']
+        self.annealing_epochs = cfg['annealing_epochs']
+        self.pc_weight = cfg['pc_weight']
+        self.rgb_s_weight = cfg['rgb_s_weight']
+        self.rgb_weight = cfg['rgb_weight']
+        self.depth_weight = cfg['depth_weight']
+        self.weight_dist_2nd_loss = cfg['weight_dist_2nd_loss']
+        self.weight_dist_1st_loss = cfg['weight_dist_1st_loss']
+        self.depth_consistency_weight = cfg['depth_consistency_weight']
+        if cfg['depth_loss_type'] != 'l1':
+            raise NotImplementedError("depth_loss_type='invariant' is not fused (default is 'l1', configs/default.yaml:102)")
+        self.loss = Loss(cfg)
+        # ---- data parallel (new component) ----
+        self.dp_group = kwargs.get('process_group', None)
+        self.dp_mode = kwargs.get('dp_mode', 'rays')        # 'rays': shard one view's rays | 'views': one view per rank
+        self.world = 1; self.rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(self.dp_group)
+            self.rank = torch.distributed.get_rank(self.dp_group)
+        self._gbuf = None
+        self._pix_cache = {}
+
+    # ------------------------------------------------------------------------------------
+    def _grad_buffer(self):
+        """[MLP 595844 | r 3V | t 3V | scales V | shifts V | loss scalars 4], zeroed, installed as .grad."""
+        V = self.pose_param_net.num_cams if self.pose_param_net is not None else 0
+        n = L.NUM_PARAMS + 8 * V + 4
+        dev = self.device
+        if self._gbuf is None or self._gbuf.numel() != n:
+            self._gbuf = torch.zeros(n, device=dev)
+        g = self._gbuf
+        g.zero_()
+        o = L.NUM_PARAMS
+        net = self.model.renderer.model
+        net.flat_grad(zero=False, alias=g[:o])
+        views = {}
+        if self.pose_param_net is not None:
+            views['r'] = g[o:o + 3 * V].view(V, 3); views['t'] = g[o + 3 * V:o + 6 * V].view(V, 3)
+            if self.pose_param_net.r.requires_grad: self.pose_param_net.r.grad = views['r']
+            if self.pose_param_net.t.requires_grad: self.pose_param_net.t.grad = views['t']
+        if self.distortion_net is not None:
+            views['scales'] = g[o + 6 * V:o + 7 * V].view(V, 1); views['shifts'] = g[o + 7 * V:o + 8 * V].view(V, 1)
+            if self.distortion_net.global_scales.requires_grad: self.distortion_net.global_scales.grad = views['scales']
+            if self.distortion_net.global_shifts.requires_grad: self.distortion_net.global_shifts.grad = views['shifts']
+        views['losses'] = g[n - 4:]
+        return g, views
+
+    def train_step(self, data, it=None, epoch=None, scheduling_start=None, render_path=None):
+        """training.py:67-97"""
+        self.model.train()
+        if self.pose_param_net: self.pose_param_net.train()
+        if self.focal_net:
+            self.focal_net.train(); self.optimizer_focal.zero_grad()
+        if self.distortion_net: self.distortion_net.train()
+        loss_dict = self.compute_loss(data, it=it, epoch=epoch, scheduling_start=scheduling_start,
+                                      out_render_path=render_path, backward=True)
+        self.optimizer.step()
+        if self.optimizer_pose: self.optimizer_pose.step()
+        if self.optimizer_focal: self.optimizer_focal.step()
+        if self.optimizer_distortion: self.optimizer_distortion.step()
+        return loss_dict
+
+    # ------------------------------------------------------------------------------------
+    def process_data_dict(self, data):
+        device = self.device
+        img = data.get('img').to(device, non_blocking=True)
+        img_idx = data.get('img.idx')
+        dpt = data.get('img.dpt').to(device, non_blocking=True).unsqueeze(1)
+        camera_mat = data.get('img.camera_mat')
+        _host_diag_check(camera_mat)
+        camera_mat = camera_mat.to(device, non_blocking=True)
+        scale_mat = data.get('img.scale_mat')
+        return (img, dpt, camera_mat, scale_mat, img_idx)
+
+    def process_data_reference(self, data):
+        device = self.device
+        ref_imgs = data.get('img.ref_imgs').to(device, non_blocking=True)
+        ref_dpts = data.get('img.ref_dpts').to(device, non_blocking=True).unsqueeze(1)
+        ref_idxs = data.get('img.ref_idxs')
+        return (ref_imgs, ref_dpts, ref_idxs)
+
+    def anneal(self, start_weight, end_weight, anneal_start_epoch, anneal_epoches, current):
+        if current <= anneal_start_epoch:
+            return start_weight
+        elif current >= anneal_start_epoch + anneal_epoches:
+            return end_weight
+        return start_weight + (end_weight - start_weight) * (current - anneal_start_epoch) / anneal_epoches
+
+    def _pixels(self, res, device):
+        key = (tuple(res), str(device))
+        if key not in self._pix_cache:
+            self._pix_cache[key] = arange_pixels(resolution=res, device=device)
+        return self._pix_cache[key]
+
+    # ------------------------------------------------------------------------------------
+    def compute_loss(self, data, eval_mode=False, it=None, epoch=None, scheduling_start=None, out_render_path=None,
+                     backward=False):
+        """training.py:197-378.  With backward=True the gradients of every learnable tensor are
+        also produced (into the flat gradient buffer, installed as .grad)."""
+        names = ['rgb_weight', 'depth_weight', 'pc_weight', 'rgb_s_weight', 'depth_consistency_weight',
+                 'weight_dist_2nd_loss', 'weight_dist_1st_loss']
+        weights = {w: self.anneal(getattr(self, w)[0], getattr(self, w)[1], scheduling_start, self.annealing_epochs, epoch)
+                   for w in names}
+        rgb_loss_type = 'l1' if epoch < self.annealing_epochs + scheduling_start else 'l2'
+        render_model = (weights['rgb_weight'] != 0.0) or (weights['depth_weight'] != 0.0)
+        use_ref_imgs = (weights['pc_weight'] != 0.0) or (weights['rgb_s_weight'] != 0.0)
+        if weights['depth_consistency_weight'] != 0.0:
+            raise NotImplementedError("depth_consistency_weight != 0 has no producer in the reference either "
+                                      "(training.py never passes d1_proj)")
+        n_points = self.n_training_points
+        (img, depth_input, camera_mat_gt, scale_mat, img_idx) = self.process_data_dict(data)
+        img_idx = int(img_idx)
+        if use_ref_imgs:
+            (ref_img, depth_ref, ref_idx) = self.process_data_reference(data)
+            ref_idx = int(ref_idx)
+        device = self.device
+        _, _, h, w = img.shape
+        _, _, h_depth, w_depth = depth_input.shape
+        net = self.model.renderer.model
+        rend = self.model.renderer
+        pose = self.pose_param_net
+        V = pose.num_cams
+        gbuf, gv = self._grad_buffer() if backward else (None, None)
+        losses4 = gv['losses'] if backward else torch.zeros(4, device=device)
+
+        # ---- focal (off by default) -------------------------------------------------------
+        fxfy = None
+        if self.optimizer_focal:
+            fxfy = self.focal_net(0)
+            z4 = torch.zeros(4, device=device); one = torch.ones(1, device=device)
+            camera_mat = torch.cat([fxfy[0:1], z4, -fxfy[1:2], z4, -one, z4, one]).view(1, 4, 4)   # training.py:247-252
+        else:
+            camera_mat = camera_mat_gt
+        cam_dev = camera_mat.detach().reshape(4, 4).contiguous().float()
+
+        # ---- distortion of the current view (distortions.py:19-27) ------------------------
+        if self.distortion_net is not None:
+            scale_input, shift_input = self.distortion_net(img_idx)
+        else:
+            scale_input = torch.ones(1, device=device); shift_input = torch.zeros(1, device=device)
+        scale_dev = scale_input.detach().reshape(1).contiguous(); shift_dev = shift_input.detach().reshape(1).contiguous()
+
+        # ---- pixel sampling (training.py:257-262), identical RNG call order to the reference ----
+        ray_idx = torch.randperm(h * w, device=device)[:n_points]
+        S = int(rend.cfg['num_points'])
+        noise = None
+        if render_model and rend.cfg['sample_option'] == 'uniform':
+            noise = torch.rand(1, n_points, S, device=device)[0]                      # rendering.py:189
+        if self.world > 1 and self.dp_mode == 'rays':                                  # shard this view's rays
+            ray_idx = ray_idx[self.rank::self.world].contiguous()
+            if noise is not None: noise = noise[self.rank::self.world].contiguous()
+        n_local = ray_idx.shape[0]
+        grad_scale = 1.0 / self.world
+
+        loss_total = torch.zeros((), device=device)
+        call = None
+        if render_model:
+            c2w = torch.empty(4, 4, device=device)
+            init = None if pose.init_c2w is None else pose.init_c2w.detach()
+            ops.pose_fwd_raw(pose.r.detach(), pose.t.detach(), init, img_idx, c2w)
+            flags = ops.flags_from_cfg(rend.cfg, net.occ_activation, eval_=eval_mode, shift_first=self.shift_first)
+            ndc = rend.cfg['sample_option'] == 'ndc'
+            call = ops.RenderCall(net.flat_weights(), c2w, cam_dev, N=n_local, S=S, flags=flags,
+                                  engine=rend.engine if rend.engine is not None else ops.default_engine(),
+                                  near=0.0 if ndc else rend.depth_range[0], far=1.0 if ndc else rend.depth_range[1],
+                                  ray_idx=ray_idx, depth_map=depth_input.detach().reshape(h_depth, w_depth).contiguous(),
+                                  scale=scale_dev, shift=shift_dev, noise=noise, H=h, W=w, stash=backward)
+            out4, g_rgb, g_dp, g_dg = ops.loss_rgb_depth(call.rgb, call.depth_pred, call.depth_gt, call.mask,
+                                                         weights['rgb_weight'], weights['depth_weight'], rgb_loss_type == 'l2',
+                                                         img=img.reshape(3, h * w), ray_idx=ray_idx, grad_scale=grad_scale)
+            losses4 += out4 * grad_scale if self.world > 1 else out4
+            if backward:
+                g_c2w = torch.zeros(4, 4, device=device)
+                g_ss = torch.zeros(2, device=device)
+                g_cam = torch.zeros(4, 4, device=device) if fxfy is not None else None
+                call.backward(g_rgb, g_dp, None if self.detach_gt_depth else g_dg, gbuf[:L.NUM_PARAMS], g_c2w, g_cam, None, g_ss)
+                ops.pose_bwd_raw(pose.r.detach(), pose.t.detach(), init, img_idx, g_c2w,
+                                 gv['r'] if pose.r.requires_grad else None, gv['t'] if pose.t.requires_grad else None)
+                # chain d/d(scale_eff, shift) into global_scales / global_shifts (clamp / fixed-last-view aware)
+                outs, gouts = [], []
+                if scale_input.requires_grad:
+                    outs.append(scale_input); gouts.append(g_ss[0:1].reshape(scale_input.shape))
+                if shift_input.requires_grad:
+                    outs.append(shift_input); gouts.append(g_ss[1:2].reshape(shift_input.shape))
+                if outs:
+                    torch.autograd.backward(outs, gouts, retain_graph=use_ref_imgs)
+                if g_cam is not None and fxfy.requires_grad:
+                    camera_mat.backward(g_cam.view(1, 4, 4), retain_graph=use_ref_imgs)
+
+        ref_terms = {}
+        if use_ref_imgs:
+            ref_loss, ref_terms = self._reference_stage(img, ref_img, depth_input, depth_ref, img_idx, ref_idx, camera_mat,
+                                                        scale_input, shift_input, weights, it, out_render_path)
+            if backward:
+                (ref_loss * grad_scale).backward()
+            loss_total = loss_total + ref_loss.detach()
+
+        # ---- data-parallel: ONE all-reduce of [grads | loss scalars] -----------------------
+        if backward and self.world > 1:
+            torch.distributed.all_reduce(gbuf, group=self.dp_group)
+        zero = torch.zeros((), device=device)
+        loss_dict = {'loss': losses4[0] + loss_total, 'loss_rgb': losses4[1], 'loss_depth': losses4[2], 'l2_mean': losses4[3],
+                     'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': ref_terms.get('loss_pc', zero),
+                     'loss_rgb_s': ref_terms.get('loss_rgb_s', zero), 'loss_depth_consistency': zero}
+        if weights['weight_dist_2nd_loss'] != 0.0 or weights['weight_dist_1st_loss'] != 0.0:
+            d1, d2 = self.loss.get_weight_dist_loss(pose.get_t())
+            extra = weights['weight_dist_1st_loss'] * d1 + weights['weight_dist_2nd_loss'] * d2
+            if backward: (extra * grad_scale).backward()
+            loss_dict['loss_dist_1st'], loss_dict['loss_dist_2nd'] = d1.detach(), d2.detach()
+            loss_dict['loss'] = loss_dict['loss'] + extra.detach()
+        if self.optimizer_focal:
+            loss_dict['focalx'] = fxfy[0] / camera_mat_gt[0, 0, 0]
+            loss_dict['focaly'] = fxfy[1] / camera_mat_gt[0, 1, 1]
+        loss_dict['scale'] = scale_input.detach()
+        loss_dict['shift'] = shift_input.detach()
+        if call is not None and not backward:
+            call.release()
+        return loss_dict
+
+    # ------------------------------------------------------------------------------------
+    def _reference_stage(self, img, ref_img, depth_input, depth_ref, img_idx, ref_idx, camera_mat, scale_input, shift_input,
+                         weights, it, out_render_path):
+        """training.py:280-365 (point-cloud + warped-RGB terms) with autograd over small tensors."""
+        device = self.device
+        pose = self.pose_param_net
+        num_cams = pose.num_cams
+        nl = self.nearest_limit
+        _, _, h_depth, w_depth = depth_input.shape
+        c2w = pose(img_idx)                                         # differentiable (nnb_pose_fwd/bwd)
+        if self.shift_first: d_in = (depth_input + shift_input) * scale_input       # training.py:241-245
+        else: d_in = depth_input * scale_input + shift_input
+        c2w_ref = pose(ref_idx)
+        if self.distortion_net is not None:
+            scale_ref, shift_ref = self.distortion_net(ref_idx)
+        else:
+            scale_ref = torch.ones(1, device=device); shift_ref = torch.zeros(1, device=device)
+        d_ref = scale_ref * (depth_ref + shift_ref) if self.shift_first else scale_ref * depth_ref + shift_ref
+        if self.detach_ref_img:
+            c2w_ref = c2w_ref.detach(); scale_ref = scale_ref.detach(); d_ref = d_ref.detach()
+        world_mat = torch.linalg.inv(c2w).unsqueeze(0)
+        ref_Rt = torch.linalg.inv(c2w_ref).unsqueeze(0)
+        if img_idx < (num_cams - 1):                                # training.py:296-313
+            d1, d2, img1, img2 = d_in, d_ref, img, ref_img
+            Rt_rel_12 = ref_Rt @ torch.linalg.inv(world_mat)
+            scale2 = scale_ref
+        else:
+            d1, d2, img1, img2 = d_ref, d_in, ref_img, img
+            Rt_rel_12 = world_mat @ torch.linalg.inv(ref_Rt)
+            scale2 = scale_input
+        R_rel_12 = Rt_rel_12[:, :3, :3]; t_rel_12 = Rt_rel_12[:, :3, 3]
+        ratio = self.pc_ratio
+        res = (int(h_depth / ratio), int(w_depth / ratio))
+        pixel_locations, p_pc = self._pixels(res, device)
+        d1 = torch.clamp(F.interpolate(d1, res, mode='nearest'), min=nl)    # training.py:318-321
+        d2 = torch.clamp(F.interpolate(d2, res, mode='nearest'), min=nl)
+        cm = camera_mat.reshape(4, 4)
+        kx, ky = cm[0, 0], cm[1, 1]
+
+        def backproject(d):                                         # transform_to_world with identity pose (common.py:112-160)
+            dd = d.reshape(1, -1)
+            return torch.stack([p_pc[..., 0] * dd / kx, p_pc[..., 1] * dd / ky, -dd], dim=-1)
+        pc1 = backproject(d1); pc2 = backproject(d2)
+        terms = {}
+        total = torch.zeros((), device=device)
+        if weights['rgb_s_weight'] != 0.0:
+            i1 = F.interpolate(img1, res, mode='bilinear'); i2 = F.interpolate(img2, res, mode='bilinear')
+            grid = p_pc.unsqueeze(1)
+            rgb_pc1 = F.grid_sample(i1, grid, mode='bilinear', align_corners=True).squeeze(2).permute(0, 2, 1)
+            src = pc1.detach().clone() if self.detach_rgbs_scale else pc1
+            pc1_rot = src @ R_rel_12.transpose(1, 2) + t_rel_12
+            invalid = (-pc1_rot[:, :, 2:] < nl).expand_as(pc1_rot)                      # training.py:334-335
+            pc1_rot = torch.where(invalid, torch.full_like(pc1_rot, nl), pc1_rot)
+            xy = torch.stack([kx * pc1_rot[..., 0], ky * pc1_rot[..., 1]], -1) / (-pc1_rot[..., 2:])   # common.py:436-457
+            valid = (xy.abs().max(dim=-1)[0] <= 1).unsqueeze(-1)
+            rgb_proj = F.grid_sample(i2, xy.unsqueeze(1), mode='bilinear', align_corners=True).squeeze(2).permute(0, 2, 1)
+            l = self.loss.get_rgb_s_loss(rgb_pc1, rgb_proj, valid)
+            terms['loss_rgb_s'] = l.detach(); total = total + weights['rgb_s_weight'] * l
+        if weights['pc_weight'] != 0.0:
+            X = pc1 @ R_rel_12.transpose(1, 2) + t_rel_12                             # training.py:356
+            Y = pc2
+            if self.scale_pcs:
+                X = X / scale2; Y = Y / scale2
+            l = self.loss.get_pc_loss(X, Y)
+            terms['loss_pc'] = l.detach(); total = total + weights['pc_weight'] * l
+        return total, terms
+
+    # ------------------------------------------------------------------------------------
+    def render_visdata(self, data, resolution, it, out_render_path):
+        """training.py:100-163 (nope_nerf render only; the phong geometry view is out of scope)."""
+        (img, dpt, camera_mat, scale_mat, img_idx) = self.process_data_dict(data)
+        h, w = resolution
+        c2w = self.pose_param_net(int(img_idx)).detach()
+        world_mat = torch.linalg.inv(c2w).unsqueeze(0)
+        if self.optimizer_focal:
+            fxfy = self.focal_net(0).detach()
+            camera_mat = torch.diag(torch.stack([fxfy[0], -fxfy[1], -torch.ones((), device=self.device),
+                                                 torch.ones((), device=self.device)])).unsqueeze(0)
+        p_idx = torch.arange(h * w, device=self.device)
+        _, pixels = self._pixels((h, w), self.device)
+        with torch.no_grad():
+            out = self.model(pixels, p_idx, camera_mat, world_mat, scale_mat, self.rendering_technique, add_noise=False,
+                             eval_mode=True, it=it, depth_img=dpt, img_size=(h, w))
+            rgb_pred = out['rgb'].view(h, w, 3).cpu().numpy()
+            depth = out['depth_pred'].view(h, w).cpu().numpy()
+        img_out = (rgb_pred * 255).astype(np.uint8)
+        if out_render_path is not None:
+            from PIL import Image
+            dn = np.clip(255.0 / depth.max() * (depth - depth.min()), 0, 255).astype(np.uint8)
+            Image.fromarray(dn).save(os.path.join(out_render_path, '%04d_depth.png' % int(img_idx)))
+            Image.fromarray(img_out).convert("RGB").save(os.path.join(out_render_path, '%04d_img.png' % int(img_idx)))
+        return img_out

@@ -1,0 +1,244 @@
+"""Torch-facing wrappers over the C ABI: tensors in, tensors out, everything enqueued on the
+current CUDA stream.  torch is plumbing here (device memory, streams, autograd glue);
+all arithmetic of the hot path happens in libnope_nerf_b200.so."""
+import ctypes as C
+import torch
+from . import _lib as L
+
+_DEFAULT_ENGINE = [L.ENGINE_TC]
+
+
+def set_default_engine(name):
+    _DEFAULT_ENGINE[0] = {"simt": L.ENGINE_SIMT, "tc": L.ENGINE_TC}[name]
+
+
+def default_engine():
+    return _DEFAULT_ENGINE[0]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t, name):
+    if t is not None and not t.is_cuda:
+        raise RuntimeError("nope_nerf_b200: %s must live on a CUDA device (no CPU fallback exists)" % name)
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+def flags_from_cfg(cfg, occ_activation="softplus", eval_=False, shift_first=False):
+    """cfg = the reference's cfg['rendering'] dict (configs/default.yaml:32-44)."""
+    f = 0
+    if cfg["dist_alpha"]: f |= L.DIST_ALPHA
+    if cfg["sample_option"] == "ndc": f |= L.NDC
+    elif cfg["sample_option"] != "uniform":
+        raise ValueError("sample_option must be 'uniform' or 'ndc' (model/rendering.py:98-101)")
+    if cfg["normalise_ray"]: f |= L.NORMALISE
+    if cfg["use_ray_dir"]: f |= L.USE_DIR
+    if cfg["white_background"]: f |= L.WHITE_BG
+    if occ_activation == "softplus": f |= L.SOFTPLUS
+    if eval_: f |= L.EVAL
+    if shift_first: f |= L.SHIFT_FIRST
+    if cfg.get("normal_loss", False):
+        raise NotImplementedError("rendering.normal_loss=True is outside the hot path (SURVEY.md 8(f) rank 4)")
+    if cfg.get("outside_steps", 0) != 0:
+        raise NotImplementedError("rendering.outside_steps != 0 is not supported")
+    return f
+
+
+class _WorkspacePool:
+    def __init__(self):
+        self.free = {}
+
+    def take(self, nbytes, device):
+        key = (nbytes, device.index)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+
+    def give(self, ws):
+        self.free.setdefault((ws.numel(), ws.device.index), []).append(ws)
+
+
+_pool = _WorkspacePool()
+
+
+class RenderCall:
+    """One forward launch + the state its backward needs (workspace with the stash)."""
+
+    def __init__(self, weights, c2w, cam, *, N, S, flags, engine, near, far, ray_idx=None, pixels=None, depth=None,
+                 depth_map=None, scale=None, shift=None, noise=None, H=0, W=0, want_z_alpha=False, stash=False):
+        for n_, t_ in (("weights", weights), ("c2w", c2w), ("camera_mat", cam), ("ray_idx", ray_idx), ("pixels", pixels),
+                       ("depth", depth), ("depth_map", depth_map), ("noise", noise)):
+            _need_cuda(t_, n_)
+        dev = weights.device
+        self.keep = [weights, c2w, cam, ray_idx, pixels, depth, depth_map, scale, shift, noise]
+        a = L.RenderArgs()
+        a.weights = L.ptr(weights); a.c2w = L.ptr(c2w); a.cam = L.ptr(cam)
+        a.ray_idx = L.ptr(ray_idx); a.pixels = L.ptr(pixels); a.depth = L.ptr(depth); a.depth_map = L.ptr(depth_map)
+        a.scale = L.ptr(scale); a.shift = L.ptr(shift); a.noise = L.ptr(noise)
+        a.N, a.S, a.H, a.W = N, S, H, W
+        if depth_map is not None:
+            a.h_d, a.w_d = depth_map.shape[-2], depth_map.shape[-1]
+        a.near_, a.far_ = float(near), float(far)
+        if stash: flags |= L.STASH
+        a.flags = flags; a.engine = engine
+        self.rgb = torch.empty(N, 3, device=dev); self.depth_pred = torch.empty(N, device=dev)
+        self.depth_gt = torch.empty(N, device=dev); self.mask = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.z_vals = torch.empty(N, S, device=dev) if want_z_alpha else None
+        self.alpha = torch.empty(N, S, device=dev) if want_z_alpha else None
+        a.rgb = L.ptr(self.rgb); a.depth_pred = L.ptr(self.depth_pred); a.depth_gt = L.ptr(self.depth_gt)
+        a.mask = L.ptr(self.mask); a.z_vals = L.ptr(self.z_vals); a.alpha = L.ptr(self.alpha)
+        nbytes = L.lib.nnb_workspace_bytes(N, S, flags, engine)
+        self.ws = _pool.take(nbytes, dev)
+        a.workspace = L.ptr(self.ws); a.workspace_bytes = self.ws.numel()
+        self.args = a; self.N = N; self.S = S; self.stash = stash
+        L.check(L.lib.nnb_render_fwd(C.byref(a), _stream()), "nnb_render_fwd")
+        if not stash:
+            self.release()
+
+    def release(self):
+        if self.ws is not None:
+            _pool.give(self.ws); self.ws = None
+
+    def backward(self, g_rgb, g_depth_pred, g_depth_gt, g_weights, g_c2w, g_cam=None, g_depth=None, g_scale_shift=None):
+        """all outputs are accumulated into (caller-zeroed) buffers; g_weights may be None (pose only)."""
+        if self.ws is None:
+            raise RuntimeError("backward called without a stashed forward")
+        b = L.RenderBwdArgs()
+        b.fwd = self.args
+        keep = [_f32c(g_rgb), _f32c(g_depth_pred), _f32c(g_depth_gt)]
+        b.g_rgb, b.g_depth_pred, b.g_depth_gt = L.ptr(keep[0]), L.ptr(keep[1]), L.ptr(keep[2])
+        b.g_weights = L.ptr(g_weights); b.g_c2w = L.ptr(g_c2w); b.g_cam = L.ptr(g_cam); b.g_depth = L.ptr(g_depth)
+        b.g_scale_shift = L.ptr(g_scale_shift)
+        L.check(L.lib.nnb_render_bwd(C.byref(b), _stream()), "nnb_render_bwd")
+        self.release()
+
+
+class _RenderFn(torch.autograd.Function):
+    """autograd glue for the drop-in Renderer / nope_nerf modules.
+    differentiable inputs: c2w (4,4), cam (4,4), depth (N,) | (scale, shift) and the 24 MLP parameters."""
+
+    @staticmethod
+    def forward(ctx, meta, flat, c2w, cam, depth, scale, shift, *params):
+        need_grad = torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (c2w, cam, depth, scale, shift) + tuple(params))
+        call = RenderCall(flat, _f32c(c2w.detach()), _f32c(cam.detach()), stash=need_grad,
+                          depth=None if depth is None else _f32c(depth.detach()),
+                          scale=None if scale is None else _f32c(scale.detach()),
+                          shift=None if shift is None else _f32c(shift.detach()), **meta)
+        ctx.call = call; ctx.nparams = len(params)
+        ctx.has = (depth is not None, scale is not None, shift is not None)
+        ctx.params_need = any(p.requires_grad for p in params)
+        ctx.mark_non_differentiable(call.mask)
+        outs = (call.rgb, call.depth_pred, call.depth_gt, call.mask)
+        if call.z_vals is not None:
+            ctx.mark_non_differentiable(call.z_vals, call.alpha)
+            outs += (call.z_vals, call.alpha)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_dp, g_dg, *unused):
+        call = ctx.call
+        dev = call.rgb.device
+        if g_rgb is None: g_rgb = torch.zeros(call.N, 3, device=dev)
+        g_c2w = torch.zeros(4, 4, device=dev); g_cam = torch.zeros(4, 4, device=dev)
+        g_w = torch.zeros(L.NUM_PARAMS, device=dev) if ctx.params_need else None
+        has_depth, has_scale, has_shift = ctx.has
+        g_depth = torch.empty(call.N, device=dev) if has_depth else None
+        g_ss = torch.zeros(2, device=dev) if (has_scale or has_shift) else None
+        call.backward(g_rgb, g_dp, g_dg, g_w, g_c2w, g_cam, g_depth, g_ss)
+        gp = [None] * ctx.nparams
+        if g_w is not None:
+            from .model.official_nerf import PARAM_SLICES
+            gp = [g_w[o:o + n].view(shape) for (o, n, shape) in PARAM_SLICES]
+        return (None, None, g_c2w, g_cam, g_depth, g_ss[0] if has_scale else None, g_ss[1] if has_shift else None) + tuple(gp)
+
+
+def render_autograd(meta, flat, c2w, cam, depth, scale, shift, params):
+    return _RenderFn.apply(meta, flat, c2w, cam, depth, scale, shift, *params)
+
+
+class _PoseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r, t, init, cam_id):
+        c2w = torch.empty(4, 4, device=r.device)
+        L.check(L.lib.nnb_pose_fwd(L.ptr(r), L.ptr(t), L.ptr(init), cam_id, L.ptr(c2w), _stream()), "nnb_pose_fwd")
+        ctx.save_for_backward(r, t, init if init is not None else r.new_empty(0))
+        ctx.cam_id = cam_id; ctx.has_init = init is not None
+        return c2w
+
+    @staticmethod
+    def backward(ctx, g):
+        r, t, init = ctx.saved_tensors
+        g_r = torch.zeros_like(r) if ctx.needs_input_grad[0] else None
+        g_t = torch.zeros_like(t) if ctx.needs_input_grad[1] else None
+        L.check(L.lib.nnb_pose_bwd(L.ptr(r), L.ptr(t), L.ptr(init) if ctx.has_init else None, ctx.cam_id, L.ptr(_f32c(g)),
+                                   L.ptr(g_r), L.ptr(g_t), _stream()), "nnb_pose_bwd")
+        return g_r, g_t, None, None
+
+
+def pose_c2w(r, t, init, cam_id):
+    _need_cuda(r, "LearnPose.r")
+    return _PoseFn.apply(r, t, init, int(cam_id))
+
+
+def pose_fwd_raw(r, t, init, cam_id, out):
+    L.check(L.lib.nnb_pose_fwd(L.ptr(r), L.ptr(t), L.ptr(init), int(cam_id), L.ptr(out), _stream()), "nnb_pose_fwd")
+
+
+def pose_bwd_raw(r, t, init, cam_id, g_c2w, g_r, g_t):
+    L.check(L.lib.nnb_pose_bwd(L.ptr(r), L.ptr(t), L.ptr(init), int(cam_id), L.ptr(g_c2w), L.ptr(g_r), L.ptr(g_t), _stream()),
+            "nnb_pose_bwd")
+
+
+def loss_rgb_depth(rgb, depth_pred, depth_gt, mask, w_rgb, w_depth, rgb_l2, *, rgb_gt=None, img=None, ray_idx=None,
+                   grad_scale=1.0):
+    """returns (losses[4] = loss, loss_rgb, loss_depth, l2_mean ; g_rgb, g_depth_pred, g_depth_gt)"""
+    N = rgb.shape[0]; dev = rgb.device
+    out = torch.empty(4, device=dev)
+    g_rgb = torch.empty(N, 3, device=dev); g_dp = torch.empty(N, device=dev); g_dg = torch.empty(N, device=dev)
+    HW = 0 if img is None else img.shape[-1] * img.shape[-2]
+    L.check(L.lib.nnb_loss_rgb_depth(L.ptr(rgb), L.ptr(rgb_gt), L.ptr(img), L.ptr(ray_idx), HW, L.ptr(depth_pred), L.ptr(depth_gt),
+                                     L.ptr(mask), N, float(w_rgb), float(w_depth), int(bool(rgb_l2)), float(grad_scale), L.ptr(out),
+                                     L.ptr(g_rgb), L.ptr(g_dp), L.ptr(g_dg), _stream()), "nnb_loss_rgb_depth")
+    return out, g_rgb, g_dp, g_dg
+
+
+class _ChamferFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, Y):
+        X = _f32c(X); Y = _f32c(Y)
+        P, Q = X.shape[0], Y.shape[0]
+        ixy = torch.empty(P, dtype=torch.int32, device=X.device); iyx = torch.empty(Q, dtype=torch.int32, device=X.device)
+        loss = torch.zeros(1, device=X.device)
+        need = X.requires_grad or Y.requires_grad
+        gX = torch.zeros_like(X) if need else None; gY = torch.zeros_like(Y) if need else None
+        L.check(L.lib.nnb_chamfer(L.ptr(X), P, L.ptr(Y), Q, L.ptr(ixy), L.ptr(iyx), L.ptr(loss), 1.0, L.ptr(gX), L.ptr(gY),
+                                  _stream()), "nnb_chamfer")
+        ctx.save_for_backward(gX if need else X.new_empty(0), gY if need else X.new_empty(0))
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gX, gY = ctx.saved_tensors
+        return (gX * g if ctx.needs_input_grad[0] else None), (gY * g if ctx.needs_input_grad[1] else None)
+
+
+def chamfer(X, Y):
+    """Loss.get_pc_loss (dense) for X (P,3), Y (Q,3) on the GPU."""
+    _need_cuda(X, "X")
+    return _ChamferFn.apply(X, Y)
+
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    L.check(L.lib.nnb_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), int(step), float(lr), beta1, beta2, eps,
+                                _stream()), "nnb_adam_step")

