@@ -81,6 +81,14 @@ typedef struct nnb_render_bwd_args {
 
 const char* nnb_last_error(void);
 int nnb_version(void);
+/* Profiling hook used by bench.py: `events` is a HOST array of cudaEvent_t handles that stays alive until
+ * nnb_profile_events(NULL,0).  Every nnb_render_fwd records 4 marks (start, weights imaged, field done,
+ * composited) and every nnb_render_bwd 5 marks (start, compositing adjoint, data-gradient chain,
+ * weight gradients, ray adjoint) on the call's stream, consuming the array in order. */
+int nnb_profile_events(void** events, int32_t count);
+int nnb_profile_cursor(void);
+/* test aid: byte offsets of the workspace sections {records, h0..h7, feat, hr, enc, denc, total} */
+int nnb_debug_layout(int32_t N, int32_t S, uint32_t flags, int32_t engine, size_t* out14);
 /* bytes of workspace needed by nnb_render_fwd (+bwd when NNB_STASH) */
 size_t nnb_workspace_bytes(int32_t N, int32_t S, uint32_t flags, int32_t engine);
 int nnb_render_fwd(const nnb_render_args* a, void* stream);

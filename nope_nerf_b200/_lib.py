@@ -48,6 +48,7 @@ def _load():
                                        C.c_float, _f, _f, _f, _f, C.c_void_p]
     lib.nnb_chamfer.argtypes = [_f, C.c_int32, _f, C.c_int32, _f, _f, _f, C.c_float, _f, _f, C.c_void_p]
     lib.nnb_adam_step.argtypes = [_f, _f, _f, _f, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.nnb_profile_events.argtypes = [C.c_void_p, C.c_int32]
     for name in ("nnb_refstage_fwd", "nnb_refstage_bwd"):
         if hasattr(lib, name):
             getattr(lib, name).restype = C.c_int
@@ -56,7 +57,7 @@ def _load():
 
 lib = _load()
 
-EXPORTS = ["nnb_last_error", "nnb_version", "nnb_workspace_bytes", "nnb_render_fwd", "nnb_render_bwd", "nnb_pose_fwd",
+EXPORTS = ["nnb_last_error", "nnb_version", "nnb_profile_events", "nnb_profile_cursor", "nnb_workspace_bytes", "nnb_render_fwd", "nnb_render_bwd", "nnb_pose_fwd",
            "nnb_pose_bwd", "nnb_loss_rgb_depth", "nnb_chamfer", "nnb_adam_step"]
 
 

@@ -11,6 +11,7 @@ cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cud
 cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st);
 cudaError_t tc_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
 size_t tc_workspace_extra(int N, int S, uint32_t flags);
+bool tc_supports(int S);
 #endif
 cudaError_t launch_pose_fwd(const float*, const float*, const float*, int, float*, cudaStream_t);
 cudaError_t launch_pose_bwd(const float*, const float*, const float*, int, const float*, float*, float*, cudaStream_t);
@@ -18,6 +19,13 @@ cudaError_t launch_loss(const float*, const float*, const float*, const int64_t*
                         int, float, float, int, float, float*, float*, float*, float*, cudaStream_t);
 cudaError_t launch_chamfer(const float*, int, const float*, int, int*, int*, float*, float, float*, float*, cudaStream_t);
 cudaError_t launch_adam(float*, const float*, float*, float*, int64_t, int, float, float, float, float, cudaStream_t);
+
+// optional profiling hook (bench.py): CUDA events recorded between the kernels of one call
+static cudaEvent_t* g_prof_events = nullptr;
+static int g_prof_n = 0, g_prof_i = 0;
+void nnb_prof_mark(cudaStream_t st) {
+  if (g_prof_events && g_prof_i < g_prof_n) cudaEventRecord(g_prof_events[g_prof_i++], st);
+}
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, ...) {
@@ -32,6 +40,20 @@ extern "C" {
 
 const char* nnb_last_error(void) { return g_err; }
 int nnb_version(void) { return 100; }
+int nnb_profile_events(void** events, int32_t count) {
+  g_prof_events = reinterpret_cast<cudaEvent_t*>(events); g_prof_n = events ? count : 0; g_prof_i = 0;
+  return 0;
+}
+int nnb_profile_cursor(void) { return g_prof_i; }
+// test/debug aid: byte offsets of the workspace sections {rec, h0..h7, feat, hr, enc, denc, total}
+int nnb_debug_layout(int32_t N, int32_t S, uint32_t flags, int32_t engine, size_t* out14) {
+  if (!out14 || N <= 0 || S <= 0) return fail(-3, "nnb_debug_layout: bad arguments");
+  WsLayout L = make_layout(N, S, flags, engine);
+  out14[0] = L.rec;
+  for (int l = 0; l < 8; ++l) out14[1 + l] = L.h[l];
+  out14[9] = L.feat; out14[10] = L.hr; out14[11] = L.enc; out14[12] = L.denc; out14[13] = L.total;
+  return 0;
+}
 
 size_t nnb_workspace_bytes(int32_t N, int32_t S, uint32_t flags, int32_t engine) {
   if (N <= 0 || S <= 0) return 0;
@@ -56,6 +78,9 @@ static int check_args(const nnb_render_args* a) {
   if (a->engine != NNB_ENGINE_SIMT && a->engine != NNB_ENGINE_TC) return fail(-4, "unknown engine %d", a->engine);
 #ifndef NNB_WITH_TC
   if (a->engine == NNB_ENGINE_TC) return fail(-4, "library built without the tcgen05 engine");
+#else
+  if (a->engine == NNB_ENGINE_TC && !tc_supports(a->S))
+    return fail(-4, "tcgen05 engine needs S in {32,64,128,256} (got %d); use NNB_ENGINE_SIMT", a->S);
 #endif
   size_t need = nnb_workspace_bytes(a->N, a->S, a->flags, a->engine);
   if (!a->workspace || a->workspace_bytes < need)

@@ -9,6 +9,8 @@
 //   B4 ray_bwd          : per-ray geometry adjoint -> d c2w, d K, d depth, d scale/shift
 #include "nnb_workspace.cuh"
 
+void nnb_prof_mark(cudaStream_t st);
+
 namespace {
 
 constexpr int TM = 64;         // samples per CTA tile
@@ -597,8 +599,11 @@ cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStr
     attr = true;
   }
   int tiles = (int)((L.M + TM - 1) / TM);
+  nnb_prof_mark(st); nnb_prof_mark(st);
   simt_mlp_fwd<<<tiles, 256, FWD_SMEM, st>>>(a, P, L.M, (a.flags & NNB_STASH) ? 1 : 0);
+  nnb_prof_mark(st);
   composite_fwd<<<(a.N + 7) / 8, 256, 0, st>>>(a, P.rec);
+  nnb_prof_mark(st);
   return cudaGetLastError();
 }
 
@@ -619,9 +624,12 @@ cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cud
   const nnb_render_args& a = b.fwd;
   SimtPtrs P = make_ptrs(L, a.workspace);
   int tiles = (int)((L.M + TM - 1) / TM);
+  nnb_prof_mark(st);
   composite_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gs);
+  nnb_prof_mark(st);
   const int write_dy = b.g_weights ? 1 : 0;
   simt_mlp_dgrad<<<tiles, 256, BWD_SMEM, st>>>(a, P, L.M, write_dy);
+  nnb_prof_mark(st);
   if (b.g_weights) {
     float* gw = b.g_weights;
     WJobs J{}; int nj = 0, tile = 0;
@@ -644,6 +652,8 @@ cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cud
     int msplit = (int)((L.M + 4095) / 4096); if (msplit < 1) msplit = 1; if (msplit > 16) msplit = 16;
     simt_wgrad<<<dim3(tile, msplit), 256, 0, st>>>(J, L.M, msplit);
   }
+  nnb_prof_mark(st);
   ray_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gp, P.gv);
+  nnb_prof_mark(st);
   return cudaGetLastError();
 }

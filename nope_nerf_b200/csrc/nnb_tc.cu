@@ -1,0 +1,472 @@
+// tcgen05 engine (NNB_ENGINE_TC): the whole field of a 128-sample tile evaluated by one
+// persistent, warp-specialised CTA per SM.
+//
+//   warp 0      : weight producer  - cp.async.bulk (UBLKCP) of pre-imaged fp16 hi/lo weight
+//                 k-slices (16 KB) from L2 into a 3-deep shared-memory ring, mbarrier tx-count
+//   warp 1      : MMA issuer       - one elected thread issues tcgen05.mma.kind::f16
+//                 (M=128, N=256|128, K=16) with BOTH operands from shared memory; every logical
+//                 product runs as three MMAs a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (split-fp16, 22-bit
+//                 operands, fp32 accumulation in TMEM) so results match the fp32 reference
+//   warps 2..5  : epilogue         - tcgen05.ld of the accumulator (thread = sample row), bias +
+//                 ReLU, re-split into hi/lo halves written IN PLACE as the next layer's A operand
+//                 (canonical no-swizzle K-major core-matrix layout), density / colour heads,
+//                 activation stash for the backward pass.
+//
+// Two 256-column TMEM accumulators alternate between consecutive layers and the A operand becomes
+// ready in 64-column blocks (one mbarrier each), so layer l+1's MMAs start while layer l's epilogue
+// is still converting: per layer the critical path is max(MMA, epilogue), not their sum.
+//
+// Shared memory operand layout (no swizzle, "interleaved"): element (row, k) of a [rows x K] fp16
+// operand lives at byte  (k/8) * rows*16 + row*16 + (k%8)*2 : 8x8 core matrices of 128 contiguous
+// bytes, SBO = 128 B between row-groups, LBO = rows*16 B between the two k-halves of one MMA.
+#include "nnb_workspace.cuh"
+#include <cuda_fp16.h>
+
+cudaError_t launch_composite_fwd(const nnb_render_args& a, const SampleRec* recs, cudaStream_t st);
+cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
+
+void nnb_prof_mark(cudaStream_t st);
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int NST = 3;                      // weight ring depth
+constexpr int STAGE_BYTES = 16384;          // 256 rows x 16 k x (hi + lo) fp16
+constexpr int N_GEMM = 10;                  // L0..L7, feature, rgb-hidden
+// ---- stage table: the order in which weight k-slices are consumed for one tile -----------------
+struct StageDesc { int w_off, ldw, kcol0, kvalid, nrows, img_off; };
+constexpr int N_STAGES = 4 + 3 * 16 + (4 + 16) + 3 * 16 + 16 + 16;   // 152
+__constant__ StageDesc c_stages[N_STAGES];
+constexpr size_t IMG_BYTES = (size_t)(N_STAGES - 16) * STAGE_BYTES + 16 * (STAGE_BYTES / 2);
+
+// shared memory map (bytes)
+constexpr int SM_AHI = 0, SM_ALO = 65536, SM_EHI = 131072, SM_ELO = 147456, SM_W = 163840;
+constexpr int SM_BIAS = SM_W + NST * STAGE_BYTES;             // 212992
+constexpr int BIAS_FLOATS = 8 * 256 + 256 + 256 + 384 + 4;    // trunk, feat, w_sigma, W_rgb, (b_sigma, b_rgb[3])
+constexpr int SM_RAYB = SM_BIAS + ((BIAS_FLOATS * 4 + 127) / 128) * 128;
+constexpr int SM_BAR = SM_RAYB + (4 * 128 + 4 * 32) * 4;   // per-ray bias [4][128] + direction-encoding staging [4][32]
+constexpr int SM_TOTAL = SM_BAR + 32 * 8 + 16;
+static_assert(SM_TOTAL <= 232448, "shared memory budget");
+enum { B_FULL = 0, B_EMPTY = NST, B_AREADY = 2 * NST, B_EREADY = 2 * NST + 4, B_ACCFULL = 2 * NST + 5, B_ACCEMPTY = 2 * NST + 7, B_COUNT = 2 * NST + 9 };
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory matrix descriptor: K-major, no swizzle, version 1 (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// instruction descriptor, kind::f16: D fp32, A/B fp16, both K-major (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// split 8 fp32 values into hi / lo fp16 halves (x = hi + lo to ~2^-22) and store 16 B each
+__device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
+    float r0 = v[2 * i] - __half2float(h0), r1 = v[2 * i + 1] - __half2float(h1);
+    __half2 hh = __halves2half2(h0, h1);
+    hi[i] = *reinterpret_cast<uint32_t*>(&hh);
+    lo[i] = pack_half2(r0, r1);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ---- weight imaging: fp32 (out,in) matrices -> per-stage shared-memory images (hi | lo) --------
+__global__ void tc_prep_weights(const float* __restrict__ w, unsigned char* __restrict__ img) {
+  const int s = blockIdx.x;
+  const StageDesc sd = c_stages[s];
+  unsigned char* hi = img + sd.img_off;
+  unsigned char* lo = hi + sd.nrows * 32;
+  for (int idx = threadIdx.x; idx < sd.nrows * 2; idx += blockDim.x) {
+    int n = idx % sd.nrows, ko = idx / sd.nrows;   // k-octet 0/1
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int k = sd.kcol0 + ko * 8 + j;
+      v[j] = (k < sd.kvalid) ? __ldg(w + sd.w_off + (size_t)n * sd.ldw + k) : 0.f;
+    }
+    split_store8(v, hi + ko * sd.nrows * 16 + n * 16, lo + ko * sd.nrows * 16 + n * 16);
+  }
+}
+
+struct TcStash {   // fp32 [sample][feature] stash consumed by the backward pass (layout of nnb_simt.cu)
+  float *h[8], *feat, *hr, *enc, *denc;
+};
+
+__device__ __forceinline__ void row_geometry_tc(const nnb_render_args& a, size_t m, size_t M, Ray& ray, int& n, int& i, float& z, float p[3]) {
+  size_t mm = m < M ? m : M - 1;
+  n = (int)(mm / a.S); i = (int)(mm % a.S);
+  setup_ray(a, n, ray);
+  z = sample_z(a, n, i);
+  sample_point(a, ray, z, p);
+}
+
+__global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const unsigned char* __restrict__ wimg, SampleRec* __restrict__ recs,
+                                                        TcStash st, size_t M, int n_tiles, int stash) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float* s_rayb = reinterpret_cast<float*>(smem + SM_RAYB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 32 * 8);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(BAR(B_AREADY + i), 128);
+    mbar_init(BAR(B_EREADY), 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (two 256-column fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {  // biases / small heads -> shared (weights are constant for the launch)
+    const float* w = a.weights;
+    for (int i = threadIdx.x; i < BIAS_FLOATS; i += blockDim.x) {
+      float v;
+      if (i < 2048) v = __ldg(w + nnb::b_off(i >> 8) + (i & 255));
+      else if (i < 2304) v = __ldg(w + nnb::B_FEAT + (i - 2048));
+      else if (i < 2560) v = __ldg(w + nnb::W_SIG + (i - 2304));
+      else if (i < 2944) v = __ldg(w + nnb::W_RGB + (i - 2560));
+      else if (i == 2944) v = __ldg(w + nnb::B_SIG);
+      else v = __ldg(w + nnb::B_RGB + (i - 2945));
+      s_bias[i] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int s = 0; s < N_STAGES; ++s) {
+          const int bytes = c_stages[s].nrows * 64;
+          mbar_wait(BAR(B_EMPTY + slot), phase ^ 1);
+          mbar_expect_tx(BAR(B_FULL + slot), bytes);
+          bulk_g2s(smem_u32(smem + SM_W + slot * STAGE_BYTES), wimg + c_stages[s].img_off, bytes, BAR(B_FULL + slot));
+          if (++slot == NST) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ====================================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      const uint32_t a_hi = smem_u32(smem + SM_AHI), a_lo = smem_u32(smem + SM_ALO);
+      const uint32_t e_hi = smem_u32(smem + SM_EHI), e_lo = smem_u32(smem + SM_ELO);
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int g = 0; g < N_GEMM; ++g) {
+          const int buf = g & 1;
+          const uint32_t use = (uint32_t)t * 5u + (uint32_t)(g >> 1);
+          mbar_wait(BAR(B_ACCEMPTY + buf), (use & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * 256;
+          const int N = (g == 9) ? 128 : 256;
+          const uint32_t idesc = make_idesc(128, N);
+          const uint32_t b_lbo = N * 16;
+          const int e_steps = (g == 0 || g == 4) ? 4 : 0;
+          const int a_steps = (g == 0) ? 0 : 16;
+          if (e_steps) { if (g == 0) { mbar_wait(BAR(B_EREADY), (uint32_t)t & 1u); tc_fence_after(); } }
+          uint32_t acc = 0;
+          for (int ks = 0; ks < e_steps + a_steps; ++ks) {
+            uint32_t ahi, alo;
+            if (ks < e_steps) { ahi = e_hi + ks * 4096; alo = e_lo + ks * 4096; }
+            else {
+              const int ka = ks - e_steps;
+              if ((ka & 3) == 0) {  // first k-step of a 64-column block: wait for the previous epilogue
+                const uint32_t au = (uint32_t)t * 9u + (uint32_t)(g - 1);
+                mbar_wait(BAR(B_AREADY + (ka >> 2)), au & 1u);
+                tc_fence_after();
+              }
+              ahi = a_hi + ka * 4096; alo = a_lo + ka * 4096;
+            }
+            mbar_wait(BAR(B_FULL + slot), phase);
+            tc_fence_after();
+            const uint32_t wb = smem_u32(smem + SM_W + slot * STAGE_BYTES);
+            const uint64_t dAh = make_desc(ahi, 2048, 128), dAl = make_desc(alo, 2048, 128);
+            const uint64_t dBh = make_desc(wb, b_lbo, 128), dBl = make_desc(wb + N * 32, b_lbo, 128);
+            tc_mma_f16(d_tmem, dAl, dBh, idesc, acc);
+            tc_mma_f16(d_tmem, dAh, dBl, idesc, 1u);
+            tc_mma_f16(d_tmem, dAh, dBh, idesc, 1u);
+            acc = 1u;
+            tc_commit(BAR(B_EMPTY + slot));
+            if (++slot == NST) { slot = 0; phase ^= 1; }
+          }
+          tc_commit(BAR(B_ACCFULL + buf));
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ================================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;             // sample row of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    unsigned char* A_hi = smem + SM_AHI; unsigned char* A_lo = smem + SM_ALO;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const size_t m = (size_t)tile * TILE + row;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogues are done with s_rayb
+      // ---- prologue: geometry, positional encoding -> E operand, per-ray direction bias ----
+      Ray ray; int n, i; float z, p[3];
+      row_geometry_tc(a, m, M, ray, n, i, z, p);
+      {
+        float e[64];
+        encode<10>(p, [&](int k, float v) { e[k] = v; });
+        e[63] = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb)
+          split_store8(e + kb * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
+        if (stash) {
+#pragma unroll
+          for (int k4 = 0; k4 < 16; ++k4)
+            *reinterpret_cast<float4*>(st.enc + m * 64 + k4 * 4) = make_float4(e[4 * k4], e[4 * k4 + 1], e[4 * k4 + 2], e[4 * k4 + 3]);
+        }
+      }
+      const int ray_local = (a.S >= TILE) ? 0 : row / a.S;
+      {
+        // direction-encoding term of rgb_layers.0 is constant per ray: fold it into a per-ray bias
+        float v[3], de[32];
+        view_dir(a, ray, v);
+        encode<4>(v, [&](int k, float val) { de[k] = val; });
+#pragma unroll
+        for (int k = 27; k < 32; ++k) de[k] = 0.f;
+        if (stash) {
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4)
+            *reinterpret_cast<float4*>(st.denc + m * 32 + k4 * 4) = make_float4(de[4 * k4], de[4 * k4 + 1], de[4 * k4 + 2], de[4 * k4 + 3]);
+        }
+        const bool first_of_ray = (a.S >= TILE) ? (row == 0) : (row % a.S == 0);
+        __syncwarp();
+        // rows that start a ray publish their direction encoding; then 128 threads cooperate
+        float* de_s = s_rayb;  // reuse: first 4*32 floats hold denc per local ray (then overwritten by the bias)
+        if (first_of_ray) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) de_s[512 + ray_local * 32 + k] = de[k];
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      {
+        const int nrays = (a.S >= TILE) ? 1 : TILE / a.S;
+        const float* w = a.weights;
+        for (int r = 0; r < nrays; ++r) {
+          float acc = __ldg(w + nnb::B_RGBH + row);
+#pragma unroll
+          for (int k = 0; k < 27; ++k) acc = fmaf(__ldg(w + nnb::W_RGBH + (size_t)row * 283 + 256 + k), s_rayb[512 + r * 32 + k], acc);
+          s_rayb[r * 128 + row] = acc;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(BAR(B_EREADY));
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float s_logit = 0.f, c_acc[3] = {0.f, 0.f, 0.f};
+      // ---- per-GEMM epilogues ----
+      for (int g = 0; g < N_GEMM; ++g) {
+        const int buf = g & 1;
+        const uint32_t use = (uint32_t)t * 5u + (uint32_t)(g >> 1);
+        mbar_wait(BAR(B_ACCFULL + buf), use & 1u);
+        tc_fence_after();
+        const int nchunks = (g == 9) ? 4 : 8;
+        const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
+#pragma unroll 1
+        for (int cb = 0; cb < nchunks; ++cb) {
+          uint32_t r[32];
+          tc_ld32(lane_addr + buf * 256 + cb * 32, r);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
+            v[j] = (g == 8) ? x : fmaxf(x, 0.f);
+          }
+          if (g == 7) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s_logit = fmaf(v[j], s_bias[2304 + cb * 32 + j], s_logit);
+          }
+          if (g == 9) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              c_acc[0] = fmaf(v[j], s_bias[2560 + cb * 32 + j], c_acc[0]);
+              c_acc[1] = fmaf(v[j], s_bias[2560 + 128 + cb * 32 + j], c_acc[1]);
+              c_acc[2] = fmaf(v[j], s_bias[2560 + 256 + cb * 32 + j], c_acc[2]);
+            }
+          }
+          if (stash) {
+            float* dst = (g < 8) ? st.h[g] + m * 256 : (g == 8 ? st.feat + m * 256 : st.hr + m * 128);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+          if (g < 9) {
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+              const int kblock = cb * 4 + kb;
+              split_store8(v + kb * 8, A_hi + kblock * 2048 + row * 16, A_lo + kblock * 2048 + row * 16);
+            }
+            if (cb & 1) {  // a 64-column block of the next layer's A operand is complete
+              fence_async_smem();
+              mbar_arrive(BAR(B_AREADY + (cb >> 1)));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(B_ACCEMPTY + buf));
+      }
+      // ---- heads + per-sample record ----
+      {
+        const float s = s_logit + s_bias[2944];
+        float sigma;
+        SampleRec rec;
+        rec.r = sigmoid_f(c_acc[0] + s_bias[2945]); rec.g = sigmoid_f(c_acc[1] + s_bias[2946]); rec.b = sigmoid_f(c_acc[2] + s_bias[2947]);
+        rec.a = density_act(s, a.flags, &sigma); rec.s = s; rec.z = z; rec.pad0 = 0.f; rec.pad1 = 0.f;
+        recs[m] = rec;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+bool g_stage_table_ready = false;
+
+cudaError_t upload_stage_table() {
+  if (g_stage_table_ready) return cudaSuccess;
+  StageDesc h[N_STAGES];
+  int s = 0, off = 0;
+  auto add = [&](int w_off, int ldw, int kcol0, int kvalid, int nrows) {
+    h[s].w_off = w_off; h[s].ldw = ldw; h[s].kcol0 = kcol0; h[s].kvalid = kvalid; h[s].nrows = nrows; h[s].img_off = off;
+    off += nrows * 64; ++s;
+  };
+  for (int i = 0; i < 4; ++i) add(nnb::w_off(0), 63, 16 * i, 63, 256);
+  for (int l = 1; l < 8; ++l) {
+    if (l == 4) for (int i = 0; i < 4; ++i) add(nnb::w_off(4), 319, 256 + 16 * i, 319, 256);
+    for (int i = 0; i < 16; ++i) add(nnb::w_off(l), nnb::w_ld(l), 16 * i, 256, 256);
+  }
+  for (int i = 0; i < 16; ++i) add(nnb::W_FEAT, 256, 16 * i, 256, 256);
+  for (int i = 0; i < 16; ++i) add(nnb::W_RGBH, 283, 16 * i, 256, 128);
+  if (s != N_STAGES || (size_t)off != IMG_BYTES) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyToSymbol(c_stages, h, sizeof(h));
+  if (e == cudaSuccess) g_stage_table_ready = true;
+  return e;
+}
+
+}  // namespace
+
+size_t tc_workspace_extra(int N, int S, uint32_t flags) { return align_up(IMG_BYTES, 256); }
+
+bool tc_supports(int S) { return S == 32 || S == 64 || S == 128 || S == 256; }
+
+cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st) {
+  if (!tc_supports(a.S)) return cudaErrorNotSupported;
+  cudaError_t e = upload_stage_table();
+  if (e != cudaSuccess) return e;
+  static bool attr = false;
+  static int n_sm = 0;
+  if (!attr) {
+    e = cudaFuncSetAttribute(tc_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  char* base = static_cast<char*>(a.workspace);
+  unsigned char* img = reinterpret_cast<unsigned char*>(base + L.total);
+  SampleRec* recs = reinterpret_cast<SampleRec*>(base + L.rec);
+  TcStash ts{};
+  const int stash = (a.flags & NNB_STASH) ? 1 : 0;
+  if (stash) {
+    for (int l = 0; l < 8; ++l) ts.h[l] = reinterpret_cast<float*>(base + L.h[l]);
+    ts.feat = reinterpret_cast<float*>(base + L.feat); ts.hr = reinterpret_cast<float*>(base + L.hr);
+    ts.enc = reinterpret_cast<float*>(base + L.enc); ts.denc = reinterpret_cast<float*>(base + L.denc);
+  }
+  nnb_prof_mark(st);
+  tc_prep_weights<<<N_STAGES, 256, 0, st>>>(a.weights, img);
+  nnb_prof_mark(st);
+  const int n_tiles = (int)((L.M + TILE - 1) / TILE);
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  tc_field_fwd<<<grid, 192, SM_TOTAL, st>>>(a, img, recs, ts, L.M, n_tiles, stash);
+  nnb_prof_mark(st);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = launch_composite_fwd(a, recs, st);
+  nnb_prof_mark(st);
+  return e;
+}
+
+// Backward of the TC engine: the forward stash has the SIMT engine's layout, so the exact-fp32
+// data/weight-gradient kernels consume it directly (a tcgen05 backward replaces this next).
+cudaError_t tc_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st) {
+  return simt_render_bwd(b, L, st);
+}

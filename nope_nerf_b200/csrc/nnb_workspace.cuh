@@ -26,7 +26,7 @@ inline WsLayout make_layout(int N, int S, uint32_t flags, int engine) {
   L.rec = take(L.Mpad * sizeof(SampleRec));
   if (flags & NNB_STASH) {
     L.gs = take(L.Mpad * 16); L.gp = take(L.Mpad * 16); L.gv = take(L.Mpad * 16);
-    if (engine == NNB_ENGINE_SIMT) {
+    {  // fp32 activation stash, shared by both engines (the TC forward feeds the same backward kernels)
       for (int l = 0; l < 8; ++l) L.h[l] = take(L.Mpad * 256 * 4);
       L.feat = take(L.Mpad * 256 * 4); L.hr = take(L.Mpad * 128 * 4);
       L.enc = take(L.Mpad * 64 * 4); L.denc = take(L.Mpad * 32 * 4);

@@ -271,7 +271,7 @@ class Trainer(object):
         if self.optimizer_focal:
             loss_dict['focalx'] = fxfy[0] / camera_mat_gt[0, 0, 0]
             loss_dict['focaly'] = fxfy[1] / camera_mat_gt[0, 1, 1]
-        loss_dict['scale'] = scale_input.detach()
+        loss_dict['scale'] = scale_input.detach()     # logging values (training.py:376-377)
         loss_dict['shift'] = shift_input.detach()
         if call is not None and not backward:
             call.release()

@@ -16,6 +16,16 @@ def default_engine():
     return _DEFAULT_ENGINE[0]
 
 
+def pick_engine(engine, S):
+    """the tcgen05 engine tiles 128 samples per CTA and needs S in {32,64,128,256}; other sample counts
+    run on the exact-fp32 SIMT engine (still CUDA; there is no CPU path)."""
+    if engine is None:
+        engine = _DEFAULT_ENGINE[0]
+    if engine == L.ENGINE_TC and S not in (32, 64, 128, 256):
+        return L.ENGINE_SIMT
+    return engine
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -90,6 +100,7 @@ class RenderCall:
             a.h_d, a.w_d = depth_map.shape[-2], depth_map.shape[-1]
         a.near_, a.far_ = float(near), float(far)
         if stash: flags |= L.STASH
+        engine = pick_engine(engine, S)
         a.flags = flags; a.engine = engine
         self.rgb = torch.empty(N, 3, device=dev); self.depth_pred = torch.empty(N, device=dev)
         self.depth_gt = torch.empty(N, device=dev); self.mask = torch.empty(N, dtype=torch.uint8, device=dev)
@@ -206,7 +217,7 @@ def loss_rgb_depth(rgb, depth_pred, depth_gt, mask, w_rgb, w_depth, rgb_l2, *, r
     N = rgb.shape[0]; dev = rgb.device
     out = torch.empty(4, device=dev)
     g_rgb = torch.empty(N, 3, device=dev); g_dp = torch.empty(N, device=dev); g_dg = torch.empty(N, device=dev)
-    HW = 0 if img is None else img.shape[-1] * img.shape[-2]
+    HW = 0 if img is None else (img.shape[-1] if img.dim() == 2 else img.shape[-1] * img.shape[-2])
     L.check(L.lib.nnb_loss_rgb_depth(L.ptr(rgb), L.ptr(rgb_gt), L.ptr(img), L.ptr(ray_idx), HW, L.ptr(depth_pred), L.ptr(depth_gt),
                                      L.ptr(mask), N, float(w_rgb), float(w_depth), int(bool(rgb_l2)), float(grad_scale), L.ptr(out),
                                      L.ptr(g_rgb), L.ptr(g_dp), L.ptr(g_dg), _stream()), "nnb_loss_rgb_depth")
