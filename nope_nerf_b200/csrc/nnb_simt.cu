@@ -588,8 +588,7 @@ constexpr size_t BWD_SMEM = FWD_SMEM + (TM * 64 + TM * 4) * sizeof(float);
 }  // namespace
 
 // entry points used by nnb_api.cu ------------------------------------------------------
-cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st) {
-  SimtPtrs P = make_ptrs(L, a.workspace);
+static cudaError_t simt_init() {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(simt_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
@@ -598,6 +597,13 @@ cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStr
     if (e != cudaSuccess) return e;
     attr = true;
   }
+  return cudaSuccess;
+}
+
+cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st) {
+  SimtPtrs P = make_ptrs(L, a.workspace);
+  cudaError_t e0 = simt_init();
+  if (e0 != cudaSuccess) return e0;
   int tiles = (int)((L.M + TM - 1) / TM);
   nnb_prof_mark(st); nnb_prof_mark(st);
   simt_mlp_fwd<<<tiles, 256, FWD_SMEM, st>>>(a, P, L.M, (a.flags & NNB_STASH) ? 1 : 0);
@@ -623,6 +629,8 @@ cudaError_t launch_ray_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, 
 cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st) {
   const nnb_render_args& a = b.fwd;
   SimtPtrs P = make_ptrs(L, a.workspace);
+  cudaError_t e0 = simt_init();
+  if (e0 != cudaSuccess) return e0;
   int tiles = (int)((L.M + TM - 1) / TM);
   nnb_prof_mark(st);
   composite_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gs);

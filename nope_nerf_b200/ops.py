@@ -140,8 +140,8 @@ class _RenderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, flat, c2w, cam, depth, scale, shift, *params):
-        need_grad = torch.is_grad_enabled() and any(
-            t is not None and t.requires_grad for t in (c2w, cam, depth, scale, shift) + tuple(params))
+        # (grad mode is always off inside Function.forward: decide from the inputs' requires_grad)
+        need_grad = any(ctx.needs_input_grad)
         call = RenderCall(flat, _f32c(c2w.detach()), _f32c(cam.detach()), stash=need_grad,
                           depth=None if depth is None else _f32c(depth.detach()),
                           scale=None if scale is None else _f32c(scale.detach()),
