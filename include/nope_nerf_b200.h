@@ -32,6 +32,7 @@ extern "C" {
 #define NNB_SOFTPLUS 64u    /* model.occ_activation == 'softplus' (official_nerf.py:77-80)        */
 #define NNB_SHIFT_FIRST 128u /* training.shift_first    (training.py:241-245)                     */
 #define NNB_STASH 256u      /* keep activations in the workspace for nnb_render_bwd               */
+#define NNB_TCBWD 512u      /* NNB_ENGINE_TC only: tcgen05 backward (operand-image stash) instead of the fp32 one */
 
 /* engines */
 #define NNB_ENGINE_SIMT 0 /* exact fp32 FMA path                                        */

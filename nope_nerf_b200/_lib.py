@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnope_nerf_b200.so")
 
 NUM_PARAMS = 595844
-DIST_ALPHA, NDC, NORMALISE, USE_DIR, WHITE_BG, EVAL, SOFTPLUS, SHIFT_FIRST, STASH = 1, 2, 4, 8, 16, 32, 64, 128, 256
+DIST_ALPHA, NDC, NORMALISE, USE_DIR, WHITE_BG, EVAL, SOFTPLUS, SHIFT_FIRST, STASH, TCBWD = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 ENGINE_SIMT, ENGINE_TC = 0, 1
 
 _f = C.c_void_p  # device pointers travel as integers

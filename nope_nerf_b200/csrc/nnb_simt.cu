@@ -613,6 +613,20 @@ cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStr
   return cudaGetLastError();
 }
 
+cudaError_t launch_simt_wgrad_jobs(const SmallJob* jobs, int njobs, size_t M, cudaStream_t st) {
+  WJobs J{}; int tile = 0;
+  for (int i = 0; i < njobs && i < 16; ++i) {
+    WJob& j = J.j[i];
+    j.dY = jobs[i].dY; j.ldy = jobs[i].ldy; j.Nn = jobs[i].Nn; j.X = jobs[i].X; j.ldx = jobs[i].ldx; j.Kk = jobs[i].Kk;
+    j.dW = jobs[i].dW; j.ldw = jobs[i].ldw; j.db = jobs[i].db;
+    j.tiles_k = (j.Kk + 63) / 64; j.ntiles = ((j.Nn + 63) / 64) * j.tiles_k; j.tile_start = tile; tile += j.ntiles;
+  }
+  J.njobs = njobs;
+  int msplit = (int)((M + 2047) / 2048); if (msplit < 1) msplit = 1; if (msplit > 64) msplit = 64;
+  simt_wgrad<<<dim3(tile, msplit), 256, 0, st>>>(J, M, msplit);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_composite_fwd(const nnb_render_args& a, const SampleRec* recs, cudaStream_t st) {
   composite_fwd<<<(a.N + 7) / 8, 256, 0, st>>>(a, recs);
   return cudaGetLastError();

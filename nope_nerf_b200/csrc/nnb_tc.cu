@@ -19,8 +19,7 @@
 // Shared memory operand layout (no swizzle, "interleaved"): element (row, k) of a [rows x K] fp16
 // operand lives at byte  (k/8) * rows*16 + row*16 + (k%8)*2 : 8x8 core matrices of 128 contiguous
 // bytes, SBO = 128 B between row-groups, LBO = rows*16 B between the two k-halves of one MMA.
-#include "nnb_workspace.cuh"
-#include <cuda_fp16.h>
+#include "nnb_tc_common.cuh"
 
 cudaError_t launch_composite_fwd(const nnb_render_args& a, const SampleRec* recs, cudaStream_t st);
 cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
@@ -49,88 +48,7 @@ constexpr int SM_TOTAL = SM_BAR + 32 * 8 + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 enum { B_FULL = 0, B_EMPTY = NST, B_AREADY = 2 * NST, B_EREADY = 2 * NST + 4, B_ACCFULL = 2 * NST + 5, B_ACCEMPTY = 2 * NST + 7, B_COUNT = 2 * NST + 9 };
 
-// ---- PTX wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// shared-memory matrix descriptor: K-major, no swizzle, version 1 (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
-  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
-}
-// instruction descriptor, kind::f16: D fp32, A/B fp16, both K-major (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// split 8 fp32 values into hi / lo fp16 halves (x = hi + lo to ~2^-22) and store 16 B each
-__device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-    float r0 = v[2 * i] - __half2float(h0), r1 = v[2 * i + 1] - __half2float(h1);
-    __half2 hh = __halves2half2(h0, h1);
-    hi[i] = *reinterpret_cast<uint32_t*>(&hh);
-    lo[i] = pack_half2(r0, r1);
-  }
-  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
+using namespace tcu;
 
 // ---- weight imaging: fp32 (out,in) matrices -> per-stage shared-memory images (hi | lo) --------
 __global__ void tc_prep_weights(const float* __restrict__ w, unsigned char* __restrict__ img) {
@@ -150,8 +68,9 @@ __global__ void tc_prep_weights(const float* __restrict__ w, unsigned char* __re
   }
 }
 
-struct TcStash {   // fp32 [sample][feature] stash consumed by the backward pass (layout of nnb_simt.cu)
+struct TcStash {   // fp32 [sample][feature] stash (layout of nnb_simt.cu) and, with NNB_TCBWD, operand planes + ReLU bitmasks
   float *h[8], *feat, *hr, *enc, *denc;
+  unsigned char* xp[10]; uint32_t* mask; size_t Mpad; int tcb;
 };
 
 __device__ __forceinline__ void row_geometry_tc(const nnb_render_args& a, size_t m, size_t M, Ray& ray, int& n, int& i, float& z, float p[3]) {
@@ -274,6 +193,7 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
       const size_t m = (size_t)tile * TILE + row;
+      if (st.tcb && row == 0) bulk_wait_read0();        // plane stores of the previous tile have read E / A
       asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogues are done with s_rayb
       // ---- prologue: geometry, positional encoding -> E operand, per-ray direction bias ----
       Ray ray; int n, i; float z, p[3];
@@ -285,7 +205,7 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb)
           split_store8(e + kb * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
-        if (stash) {
+        if (stash && !st.tcb) {
 #pragma unroll
           for (int k4 = 0; k4 < 16; ++k4)
             *reinterpret_cast<float4*>(st.enc + m * 64 + k4 * 4) = make_float4(e[4 * k4], e[4 * k4 + 1], e[4 * k4 + 2], e[4 * k4 + 3]);
@@ -327,6 +247,10 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
       fence_async_smem();
       mbar_arrive(BAR(B_EREADY));
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (stash && st.tcb && row == 0) {   // encoding operand image -> X plane 0
+        unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64;
+        bulk_s2g(dst, smem_u32(smem + SM_EHI), 16384); bulk_s2g(dst + 16384, smem_u32(smem + SM_ELO), 16384); bulk_commit();
+      }
       float s_logit = 0.f, c_acc[3] = {0.f, 0.f, 0.f};
       // ---- per-GEMM epilogues ----
       for (int g = 0; g < N_GEMM; ++g) {
@@ -336,6 +260,8 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         tc_fence_after();
         const int nchunks = (g == 9) ? 4 : 8;
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
+        const bool planes = stash && st.tcb;
+        if (planes && g < 9) { if (row == 0) bulk_wait_read0(); epi_bar(); }   // previous image read out before it is overwritten
 #pragma unroll 1
         for (int cb = 0; cb < nchunks; ++cb) {
           uint32_t r[32];
@@ -358,11 +284,17 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
               c_acc[2] = fmaf(v[j], s_bias[2560 + 256 + cb * 32 + j], c_acc[2]);
             }
           }
-          if (stash) {
+          if (stash && (!planes || g == 7 || g == 9)) {
             float* dst = (g < 8) ? st.h[g] + m * 256 : (g == 8 ? st.feat + m * 256 : st.hr + m * 128);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
               *reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+          if (planes && g < 8) {   // ReLU bitmask of this 32-column chunk
+            uint32_t mw = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
+            st.mask[((size_t)g * st.Mpad + m) * 8 + cb] = mw;
           }
           if (g < 9) {
 #pragma unroll
@@ -378,6 +310,13 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         }
         tc_fence_before();
         mbar_arrive(BAR(B_ACCEMPTY + buf));
+        if (planes && g < 9) {   // the finished A image (h_g, or feat for g = 8) is the X operand plane of the weight-gradient pass
+          epi_bar();
+          if (row == 0) {
+            unsigned char* dst = st.xp[1 + g] + (size_t)tile * PLANE_TILE_256;
+            bulk_s2g(dst, smem_u32(A_hi), 65536); bulk_s2g(dst + 65536, smem_u32(A_lo), 65536); bulk_commit();
+          }
+        }
       }
       // ---- heads + per-sample record ----
       {
@@ -389,6 +328,7 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         recs[m] = rec;
       }
     }
+    if (st.tcb && row == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -424,7 +364,10 @@ cudaError_t upload_stage_table() {
 
 }  // namespace
 
-size_t tc_workspace_extra(int N, int S, uint32_t flags) { return align_up(IMG_BYTES, 256); }
+size_t tc_bwd_workspace_extra();
+cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L, size_t img_t_offset, cudaStream_t st);
+
+size_t tc_workspace_extra(int N, int S, uint32_t flags) { return align_up(IMG_BYTES, 256) + tc_bwd_workspace_extra(); }
 
 bool tc_supports(int S) { return S == 32 || S == 64 || S == 128 || S == 256; }
 
@@ -447,9 +390,14 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
   TcStash ts{};
   const int stash = (a.flags & NNB_STASH) ? 1 : 0;
   if (stash) {
-    for (int l = 0; l < 8; ++l) ts.h[l] = reinterpret_cast<float*>(base + L.h[l]);
+    ts.tcb = (a.flags & NNB_TCBWD) ? 1 : 0;
+    for (int l = 0; l < 8; ++l) ts.h[l] = reinterpret_cast<float*>(base + L.h[l]);   // TCBWD: only h[7] is carved (others unused)
     ts.feat = reinterpret_cast<float*>(base + L.feat); ts.hr = reinterpret_cast<float*>(base + L.hr);
     ts.enc = reinterpret_cast<float*>(base + L.enc); ts.denc = reinterpret_cast<float*>(base + L.denc);
+    if (ts.tcb) {
+      for (int i = 0; i < 10; ++i) ts.xp[i] = reinterpret_cast<unsigned char*>(base + L.xp[i]);
+      ts.mask = reinterpret_cast<uint32_t*>(base + L.mask); ts.Mpad = L.Mpad;
+    }
   }
   nnb_prof_mark(st);
   tc_prep_weights<<<N_STAGES, 256, 0, st>>>(a.weights, img);
@@ -468,5 +416,6 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
 // Backward of the TC engine: the forward stash has the SIMT engine's layout, so the exact-fp32
 // data/weight-gradient kernels consume it directly (a tcgen05 backward replaces this next).
 cudaError_t tc_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st) {
+  if (b.fwd.flags & NNB_TCBWD) return tc_render_bwd_planes(b, L, L.total + align_up(IMG_BYTES, 256), st);
   return simt_render_bwd(b, L, st);
 }

@@ -6,6 +6,11 @@ import torch
 from . import _lib as L
 
 _DEFAULT_ENGINE = [L.ENGINE_TC]
+_TC_BACKWARD = [True]     # tcgen05 backward (operand-plane stash); False -> fp32 SIMT backward after a TC forward
+
+
+def set_tc_backward(on):
+    _TC_BACKWARD[0] = bool(on)
 
 
 def set_default_engine(name):
@@ -99,8 +104,10 @@ class RenderCall:
         if depth_map is not None:
             a.h_d, a.w_d = depth_map.shape[-2], depth_map.shape[-1]
         a.near_, a.far_ = float(near), float(far)
-        if stash: flags |= L.STASH
         engine = pick_engine(engine, S)
+        if stash:
+            flags |= L.STASH
+            if engine == L.ENGINE_TC and _TC_BACKWARD[0]: flags |= L.TCBWD
         a.flags = flags; a.engine = engine
         self.rgb = torch.empty(N, 3, device=dev); self.depth_pred = torch.empty(N, device=dev)
         self.depth_gt = torch.empty(N, device=dev); self.mask = torch.empty(N, dtype=torch.uint8, device=dev)
