@@ -270,7 +270,9 @@ __global__ void composite_fwd(nnb_render_args a, const SampleRec* recs) {
   }
 }
 
-__global__ void composite_bwd(nnb_render_bwd_args b, const SampleRec* recs, float4* gs) {
+// gmax (optional): running max |g| over all samples, as uint bits of a non-negative float
+// (feeds the power-of-two gradient scaling of the split-fp16 tcgen05 backward)
+__global__ void composite_bwd(nnb_render_bwd_args b, const SampleRec* recs, float4* gs, unsigned int* gmax) {
   const nnb_render_args& a = b.fwd;
   const int lane = threadIdx.x & 31, n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= a.N) return;
@@ -304,7 +306,7 @@ __global__ void composite_bwd(nnb_render_bwd_args b, const SampleRec* recs, floa
       dfac[c] = df;
     }
   }
-  float carry_s = 0.f;
+  float carry_s = 0.f, vmax = 0.f;
 #pragma unroll
   for (int c = MAXC - 1; c >= 0; --c) {
     if (c < C) {
@@ -315,8 +317,17 @@ __global__ void composite_bwd(nnb_render_bwd_args b, const SampleRec* recs, floa
       float suffix = excl + carry_s;
       carry_s += __shfl_sync(0xffffffffu, incl, 0);
       float g_alpha = Tm[c] * gwm[c] - suffix / omm[c];
-      if (valid) gs[(size_t)n * a.S + i] = make_float4(wm[c] * gC0, wm[c] * gC1, wm[c] * gC2, g_alpha * dfac[c]);
+      if (valid) {
+        float4 o = make_float4(wm[c] * gC0, wm[c] * gC1, wm[c] * gC2, g_alpha * dfac[c]);
+        gs[(size_t)n * a.S + i] = o;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+      }
     }
+  }
+  if (gmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && isfinite(vmax)) atomicMax(gmax, __float_as_uint(vmax));
   }
 }
 
@@ -631,8 +642,8 @@ cudaError_t launch_composite_fwd(const nnb_render_args& a, const SampleRec* recs
   composite_fwd<<<(a.N + 7) / 8, 256, 0, st>>>(a, recs);
   return cudaGetLastError();
 }
-cudaError_t launch_composite_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, float4* gs, cudaStream_t st) {
-  composite_bwd<<<(b.fwd.N + 7) / 8, 256, 0, st>>>(b, recs, gs);
+cudaError_t launch_composite_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, float4* gs, unsigned int* gmax, cudaStream_t st) {
+  composite_bwd<<<(b.fwd.N + 7) / 8, 256, 0, st>>>(b, recs, gs, gmax);
   return cudaGetLastError();
 }
 cudaError_t launch_ray_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, const float4* gp, const float4* gv, cudaStream_t st) {
@@ -647,7 +658,7 @@ cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cud
   if (e0 != cudaSuccess) return e0;
   int tiles = (int)((L.M + TM - 1) / TM);
   nnb_prof_mark(st);
-  composite_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gs);
+  composite_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gs, nullptr);
   nnb_prof_mark(st);
   const int write_dy = b.g_weights ? 1 : 0;
   simt_mlp_dgrad<<<tiles, 256, BWD_SMEM, st>>>(a, P, L.M, write_dy);

@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
       const size_t m = (size_t)tile * TILE + row;
-      if (st.tcb && row == 0) bulk_wait_read0();        // plane stores of the previous tile have read E / A
       asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogues are done with s_rayb
       // ---- prologue: geometry, positional encoding -> E operand, per-ray direction bias ----
       Ray ray; int n, i; float z, p[3];
@@ -209,6 +208,11 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
 #pragma unroll
           for (int k4 = 0; k4 < 16; ++k4)
             *reinterpret_cast<float4*>(st.enc + m * 64 + k4 * 4) = make_float4(e[4 * k4], e[4 * k4 + 1], e[4 * k4 + 2], e[4 * k4 + 3]);
+        }
+        if (stash && st.tcb) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
+          unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + row * 16;
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) split_store8_bf16(e + kb * 8, dst + kb * 2048, dst + 16384 + kb * 2048);
         }
       }
       const int ray_local = (a.S >= TILE) ? 0 : row / a.S;
@@ -247,10 +251,6 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
       fence_async_smem();
       mbar_arrive(BAR(B_EREADY));
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (stash && st.tcb && row == 0) {   // encoding operand image -> X plane 0
-        unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64;
-        bulk_s2g(dst, smem_u32(smem + SM_EHI), 16384); bulk_s2g(dst + 16384, smem_u32(smem + SM_ELO), 16384); bulk_commit();
-      }
       float s_logit = 0.f, c_acc[3] = {0.f, 0.f, 0.f};
       // ---- per-GEMM epilogues ----
       for (int g = 0; g < N_GEMM; ++g) {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         const int nchunks = (g == 9) ? 4 : 8;
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
         const bool planes = stash && st.tcb;
-        if (planes && g < 9) { if (row == 0) bulk_wait_read0(); epi_bar(); }   // previous image read out before it is overwritten
+        unsigned char* xplane = (planes && g < 9) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + row * 16 : nullptr;
 #pragma unroll 1
         for (int cb = 0; cb < nchunks; ++cb) {
           uint32_t r[32];
@@ -290,6 +290,11 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
             for (int j4 = 0; j4 < 8; ++j4)
               *reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
           }
+          if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi|lo, coalesced 512 B per warp
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+              split_store8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
+          }
           if (planes && g < 8) {   // ReLU bitmask of this 32-column chunk
             uint32_t mw = 0;
 #pragma unroll
@@ -310,13 +315,6 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         }
         tc_fence_before();
         mbar_arrive(BAR(B_ACCEMPTY + buf));
-        if (planes && g < 9) {   // the finished A image (h_g, or feat for g = 8) is the X operand plane of the weight-gradient pass
-          epi_bar();
-          if (row == 0) {
-            unsigned char* dst = st.xp[1 + g] + (size_t)tile * PLANE_TILE_256;
-            bulk_s2g(dst, smem_u32(A_hi), 65536); bulk_s2g(dst + 65536, smem_u32(A_lo), 65536); bulk_commit();
-          }
-        }
       }
       // ---- heads + per-sample record ----
       {
@@ -328,7 +326,6 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         recs[m] = rec;
       }
     }
-    if (st.tcb && row == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();

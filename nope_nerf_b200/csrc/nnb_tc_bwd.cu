@@ -16,7 +16,7 @@
 #include "nnb_tc_common.cuh"
 
 void nnb_prof_mark(cudaStream_t st);
-cudaError_t launch_composite_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, float4* gs, cudaStream_t st);
+cudaError_t launch_composite_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, float4* gs, unsigned int* gmax, cudaStream_t st);
 cudaError_t launch_ray_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, const float4* gp, const float4* gv, cudaStream_t st);
 cudaError_t launch_simt_wgrad_jobs(const SmallJob* jobs, int njobs, size_t M, cudaStream_t st);
 
@@ -61,7 +61,7 @@ __global__ void tc_prep_weights_T(const float* __restrict__ w, unsigned char* __
       int n = sd.n0 + no * 8 + j;
       v[j] = (n < sd.nvalid && sd.kcol0 + k < sd.kvalid) ? __ldg(w + sd.w_off + (size_t)n * sd.ldw + sd.kcol0 + k) : 0.f;
     }
-    split_store8(v, hi + no * sd.nrows * 16 + k * 16, lo + no * sd.nrows * 16 + k * 16);
+    split_store8_bf16(v, hi + no * sd.nrows * 16 + k * 16, lo + no * sd.nrows * 16 + k * 16);   // backward runs in bf16 hi|lo
   }
 }
 
@@ -69,8 +69,20 @@ struct DgradPtrs {
   const SampleRec* rec; const float4* gs; float4* gp; float4* dyc;
   const float* hr; float* dyr; const uint32_t* mask;       // fp32 side stashes, ReLU bitmasks
   unsigned char* dyp[10];                                    // dY operand planes
+  const unsigned int* gmax;                                  // max |g| bits -> power-of-two gradient scale
   size_t Mpad;
 };
+
+// (GBF = false experiment: fp16 keeps a 22-bit hi/lo split only for |x| >~ 1, so the chain would run on
+// g * 2^k with the largest incoming cotangent at 2^8.  Gradients decay by ~5 orders of magnitude along the
+// chain, which fp16 cannot follow with one global scale, and tcgen05 kind::f16 traps on mixed fp16/bf16
+// operands — hence the shipped backward is bf16 hi|lo throughout, GBF = true.)
+__device__ __forceinline__ float grad_scale_from(const unsigned int* gmax) {
+  float m = __uint_as_float(*gmax);
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e; frexpf(m, &e);            // m = f * 2^e, f in [0.5,1)
+  return ldexpf(1.f, 8 - e);
+}
 
 __device__ __forceinline__ void row_geometry_b(const nnb_render_args& a, size_t m, size_t M, Ray& ray, int& n, int& i, float& z, float p[3]) {
   size_t mm = m < M ? m : M - 1;
@@ -80,6 +92,7 @@ __device__ __forceinline__ void row_geometry_b(const nnb_render_args& a, size_t 
   sample_point(a, ray, z, p);
 }
 
+template <bool GBF>
 __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsigned char* __restrict__ wimg, DgradPtrs P, size_t M,
                                                     int n_tiles, int write_dy) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -107,6 +120,10 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const float gscale = GBF ? 1.f : grad_scale_from(P.gmax), inv_gscale = 1.f / gscale;
+  auto split_g = [&](const float* v, unsigned char* hi, unsigned char* lo) {
+    if (GBF) split_store8_bf16(v, hi, lo); else split_store8(v, hi, lo);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -132,7 +149,7 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
           tc_fence_after();
           const int N = c_pos_N[pos], ksteps = c_pos_ksteps[pos];
           const uint32_t d_tmem = tmem_base + buf * 256;
-          const uint32_t idesc = make_idesc(128, N);
+          const uint32_t idesc = make_idesc_ex(128, N, 1, 1, 0, 0);   // A = gradients, B = transposed weights, both bf16 hi|lo, K-major
           const uint32_t b_lbo = N * 16;
           const uint32_t aver = (uint32_t)t * 10u + (uint32_t)c_pos_aver[pos];
           uint32_t acc = 0;
@@ -174,7 +191,8 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
         SampleRec rec = P.rec[m];
         float gyc0 = g.x * rec.r * (1.f - rec.r), gyc1 = g.y * rec.g * (1.f - rec.g), gyc2 = g.z * rec.b * (1.f - rec.b);
         g_s = g.w * density_act_grad(rec.s, a.flags);
-        P.dyc[m] = make_float4(gyc0, gyc1, gyc2, g_s);
+        P.dyc[m] = make_float4(gyc0, gyc1, gyc2, g_s);          // fp32 side stash stays unscaled
+        gyc0 *= gscale; gyc1 *= gscale; gyc2 *= gscale; g_s *= gscale;
         const float* hr = P.hr + m * 128;
         float* dyr = P.dyr + m * 128;
 #pragma unroll 1
@@ -186,9 +204,9 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
             float x = gyc0 * s_small[jb * 8 + j] + gyc1 * s_small[128 + jb * 8 + j] + gyc2 * s_small[256 + jb * 8 + j];
             v[j] = hv[j] > 0.f ? x : 0.f;
           }
-          split_store8(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16);
-          *reinterpret_cast<float4*>(dyr + jb * 8) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dyr + jb * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          split_g(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16);
+          *reinterpret_cast<float4*>(dyr + jb * 8) = make_float4(v[0] * inv_gscale, v[1] * inv_gscale, v[2] * inv_gscale, v[3] * inv_gscale);
+          *reinterpret_cast<float4*>(dyr + jb * 8 + 4) = make_float4(v[4] * inv_gscale, v[5] * inv_gscale, v[6] * inv_gscale, v[7] * inv_gscale);
         }
       }
       fence_async_smem();
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
           } else {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
-              split_store8(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16);
+              split_g(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16);
             if (cb & 1) { fence_async_smem(); mbar_arrive(BAR(D_AREADY + (cb >> 1))); }
           }
         }
@@ -253,7 +271,7 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
         Ray ray; int n, i; float z, p[3], gp[3];
         row_geometry_b(a, m, M, ray, n, i, z, p);
         encode_bwd<10>(p, [&](int k) { return s_genc[k * 128 + row]; }, gp);
-        P.gp[m] = make_float4(gp[0], gp[1], gp[2], 0.f);
+        P.gp[m] = make_float4(gp[0] * inv_gscale, gp[1] * inv_gscale, gp[2] * inv_gscale, 0.f);
       }
     }
     if (row == 0) bulk_wait0();
@@ -285,9 +303,14 @@ constexpr int WG_SLOT = 32768, WG_NSLOT = 6;
 constexpr int WG_ONES = WG_NSLOT * WG_SLOT;          // 512 B ones operand
 constexpr int WG_BAR = WG_ONES + 512;
 constexpr int WG_TOTAL = WG_BAR + 16 * 8 + 16;
-enum { G_FULL = 0, G_EMPTY = 6, G_DONE = 12 };
+enum { G_FULL = 0, G_EMPTY = 6, G_DONE = 12, G_DRAINED = 13 };
+// The tensor core adds each K=16 partial product to the fp32 accumulator with truncation, so the error of a long
+// accumulation chain grows linearly (~3e-8 per MMA, measured 2.9e-4 at ~2000 MMAs).  The accumulator is therefore
+// drained to the fp32 gradient buffer every WG_GROUP tiles (24 MMAs each) and restarted from zero.
+constexpr int WG_GROUP = 16;
 
-__global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restrict__ gflat) {
+template <bool GBF>
+__global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restrict__ gflat, const unsigned int* __restrict__ gmax) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const WgJob J = jobs.j[blockIdx.x / jobs.msplit];
@@ -300,7 +323,7 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   if (threadIdx.x == 0) {
     for (int i = 0; i < WG_NSLOT; ++i) { mbar_init(BAR(G_FULL + i), 1); mbar_init(BAR(G_EMPTY + i), 1); }
-    mbar_init(BAR(G_DONE), 1);
+    mbar_init(BAR(G_DONE), 1); mbar_init(BAR(G_DRAINED), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -308,8 +331,8 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x < 128) {   // ones operand: [2 n'-blocks][16 samples][8] fp16, (m, n'=0) = 1
-    __half* o = reinterpret_cast<__half*>(smem + WG_ONES);
-    for (int i = threadIdx.x; i < 256; i += 128) o[i] = __float2half((i < 128 && (i & 7) == 0) ? 1.f : 0.f);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(smem + WG_ONES);
+    for (int i = threadIdx.x; i < 256; i += 128) o[i] = __float2bfloat16((i < 128 && (i & 7) == 0) ? 1.f : 0.f);
   }
   fence_async_smem();
   tc_fence_before();
@@ -340,11 +363,12 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_mn(128, J.N), idesc1 = make_idesc_mn(128, 16);
+      // A = dY planes, B = activation planes / ones: all bf16 hi|lo, MN-major (tcgen05 kind::f16 needs one format for A and B)
+      const uint32_t idesc = make_idesc_ex(128, J.N, 1, 1, 1, 1), idesc1 = make_idesc_ex(128, 16, 1, 1, 1, 1);
       const uint32_t s0 = smem_u32(smem), ones = smem_u32(smem + WG_ONES);
       const uint32_t d_main = tmem_base, d_bias = tmem_base + 256;
       const uint32_t xsbo = big ? 2048u : 2048u;
-      uint32_t first = 0;
+      uint32_t first = 0, gphase = 0;
       for (int t = t0; t < t1; ++t) {
         // products: (A_hi,B_hi) (A_hi,B_lo) (A_lo,B_hi); A = slot0 / slot5, B_hi = slot1(+2), B_lo = slot3(+4)
         mbar_wait(BAR(G_FULL + 0), phase); mbar_wait(BAR(G_FULL + 1), phase); if (big) mbar_wait(BAR(G_FULL + 2), phase);
@@ -371,15 +395,20 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
         }
         tc_commit(BAR(G_EMPTY + 1)); if (big) tc_commit(BAR(G_EMPTY + 2)); tc_commit(BAR(G_EMPTY + 5));
         phase ^= 1;
+        if (((t - t0 + 1) % WG_GROUP) == 0 || t + 1 == t1) {   // hand the accumulator to the epilogue warps, restart from zero
+          tc_commit(BAR(G_DONE));
+          if (t + 1 < t1) { mbar_wait(BAR(G_DRAINED), gphase); tc_fence_after(); gphase ^= 1; first = 0; }
+        }
       }
-      tc_commit(BAR(G_DONE));
     }
   } else {
     const int q = warp & 3, row = q * 32 + lane;
-    if (t1 > t0) {
-      mbar_wait(BAR(G_DONE), 0);
+    const int ngroups = (t1 - t0 + WG_GROUP - 1) / WG_GROUP;
+    for (int gi = 0; gi < ngroups; ++gi) {
+      mbar_wait(BAR(G_DONE), (uint32_t)gi & 1u);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const float inv_gscale = GBF ? 1.f : 1.f / grad_scale_from(gmax);     // fp16 dY planes carry the chain's power-of-two scale
       float* dst = gflat + J.w_off + (size_t)(J.n_base + row) * J.ldw;
       const int nchunks = J.N / 32;
       for (int cb = 0; cb < nchunks; ++cb) {
@@ -388,14 +417,16 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int k = cb * 32 + j;
-          if (k < J.kvalid) atomicAdd(dst + k, __uint_as_float(r[j]));
+          if (k < J.kvalid) atomicAdd(dst + k, __uint_as_float(r[j]) * inv_gscale);
         }
       }
       if (J.b_off >= 0) {
         uint32_t r[32];
         tc_ld32(lane_addr + 256, r);
-        atomicAdd(gflat + J.b_off + J.n_base + row, __uint_as_float(r[0]));
+        atomicAdd(gflat + J.b_off + J.n_base + row, __uint_as_float(r[0]) * inv_gscale);
       }
+      tc_fence_before();
+      mbar_arrive(BAR(G_DRAINED));
     }
   }
   tc_fence_before();
@@ -469,9 +500,9 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   static bool attr = false;
   static int n_sm = 0;
   if (!attr) {
-    e = cudaFuncSetAttribute(tc_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL);
+    e = cudaFuncSetAttribute(tc_dgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_TOTAL);
+    e = cudaFuncSetAttribute(tc_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_TOTAL);
     if (e != cudaSuccess) return e;
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -483,8 +514,11 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   float4* gp = reinterpret_cast<float4*>(base + L.gp);
   float4* gv = reinterpret_cast<float4*>(base + L.gv);
   unsigned char* img_t = reinterpret_cast<unsigned char*>(base + img_t_offset);
+  unsigned int* gmax = reinterpret_cast<unsigned int*>(base + L.gmax);
+  e = cudaMemsetAsync(gmax, 0, 4, st);
+  if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
-  e = launch_composite_bwd(b, recs, gs, st);
+  e = launch_composite_bwd(b, recs, gs, gmax, st);
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
   tc_prep_weights_T<<<N_STAGES_T, 256, 0, st>>>(a.weights, img_t);
@@ -493,10 +527,11 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   P.hr = reinterpret_cast<const float*>(base + L.hr); P.dyr = reinterpret_cast<float*>(base + L.dyr);
   P.mask = reinterpret_cast<const uint32_t*>(base + L.mask);
   for (int i = 0; i < 10; ++i) P.dyp[i] = reinterpret_cast<unsigned char*>(base + L.dyp[i]);
-  P.Mpad = L.Mpad;
+  P.Mpad = L.Mpad; P.gmax = gmax;
   const int n_tiles = (int)L.n_tiles;
   const int write_dy = b.g_weights ? 1 : 0;
-  tc_dgrad<<<n_tiles < n_sm ? n_tiles : n_sm, 192, DG_TOTAL, st>>>(a, img_t, P, L.M, n_tiles, write_dy);
+  const int grid_d = n_tiles < n_sm ? n_tiles : n_sm;
+  tc_dgrad<true><<<grid_d, 192, DG_TOTAL, st>>>(a, img_t, P, L.M, n_tiles, write_dy);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
@@ -521,7 +556,7 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
     J.njobs = nj; J.n_tiles = n_tiles;
     int msplit = n_sm / nj; if (msplit < 1) msplit = 1; if (msplit > n_tiles) msplit = n_tiles;
     J.msplit = msplit;
-    tc_wgrad<<<nj * msplit, 192, WG_TOTAL, st>>>(J, b.g_weights);
+    tc_wgrad<true><<<nj * msplit, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     SmallJob sj[3];

@@ -3,6 +3,7 @@
 #pragma once
 #include "nnb_workspace.cuh"
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 
 namespace tcu {
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -89,6 +90,27 @@ __device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_d
 }
 
 
+// bf16 hi/lo split (x = hi + lo to ~2^-17, full fp32 exponent range): used for GRADIENT operands, whose
+// magnitudes decay by orders of magnitude along the backward chain (fp16 would run into subnormals)
+__device__ __forceinline__ void split_store8_bf16(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    float r0 = v[2 * i] - __bfloat162float(h0), r1 = v[2 * i + 1] - __bfloat162float(h1);
+    __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+    hi[i] = *reinterpret_cast<uint32_t*>(&hh);
+    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// instruction descriptor with explicit operand formats (0 = fp16, 1 = bf16) and major-ness (0 = K, 1 = MN)
+__host__ __device__ constexpr uint32_t make_idesc_ex(int M, int N, int afmt, int bfmt, int amaj, int bmaj) {
+  return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)amaj << 15) | ((uint32_t)bmaj << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // MN-major, no swizzle (cute::UMMA canonical "INTERLEAVE" MN layout): lbo = byte stride between core
 // matrices along K (the reduction), sbo = byte stride between 8-element groups along M/N.
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {   // both operands MN-major

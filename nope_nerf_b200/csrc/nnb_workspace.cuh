@@ -18,6 +18,7 @@ struct WsLayout {
   size_t xp[10];    // X planes: 0 = enc (64 feat), 1..8 = h0..h7, 9 = feat
   size_t dyp[10];   // dY planes: 0..7 = dy0..dy7, 8 = dfeat, 9 = dyr (128 feat)
   size_t mask;      // uint32 [8 layers][Mpad][8]
+  size_t gmax;      // uint32 bits of max |g| (gradient scaling)
   size_t total;  // bytes
 };
 constexpr size_t PLANE_TILE_256 = 131072, PLANE_TILE_128 = 65536, PLANE_TILE_64 = 32768;
@@ -46,6 +47,7 @@ inline WsLayout make_layout(int N, int S, uint32_t flags, int engine) {
       for (int i = 0; i < 9; ++i) L.dyp[i] = take(L.n_tiles * PLANE_TILE_256);
       L.dyp[9] = take(L.n_tiles * PLANE_TILE_128);
       L.mask = take(L.Mpad * 8 * 8 * 4);
+      L.gmax = take(256);
     } else {  // fp32 [sample][feature] stash (SIMT backward; also consumed after a TC forward)
       for (int l = 0; l < 8; ++l) L.h[l] = take(L.Mpad * 256 * 4);
       L.feat = take(L.Mpad * 256 * 4); L.hr = take(L.Mpad * 128 * 4);

@@ -46,3 +46,21 @@ for name in ("tc+simt", "tc+tc"):
     for n in O.PARAM_NAMES:
         den = np.abs(Pr[n]).max(); err = np.abs(Pr[n] - Pb[n]).max()
         print("  %-22s max|ref| %.3e rel %.3e nan %d" % (n, den, err / max(den, 1e-30), int(np.isnan(Pb[n]).sum())))
+
+if N <= 128:
+    # fp64 truth from the oracle on the same inputs
+    P64 = {k: v.astype(np.float64) for k, v in O.init_params(seed=5).items()}
+    pix = O.pixels_from_idx(ray_idx.cpu().numpy(), H, W, np.float64)
+    raw, _ = O.gather_prior_depth(dpt.cpu().numpy(), ray_idx.cpu().numpy(), H, W)
+    cfg["num_points"] = S
+    out, cache = O.render_forward(P64, pix, raw.astype(np.float64), c2w.cpu().numpy().astype(np.float64), 1.2, -1.6, cfg,
+                                  noise=noise.cpu().numpy().astype(np.float64))
+    gr = O.render_backward(P64, cache, g_rgb.cpu().numpy().astype(np.float64), g_dp.cpu().numpy().astype(np.float64),
+                           g_dg.cpu().numpy().astype(np.float64))
+    print("== vs fp64 oracle (rel to tensor max):  simt | tc+simt | tc+tc")
+    for n in O.PARAM_NAMES:
+        den = np.abs(gr["params"][n]).max()
+        errs = [np.abs(O.unflatten_params(res[k]["w"])[n] - gr["params"][n]).max() / den for k in ("simt", "tc+simt", "tc+tc")]
+        print("  %-22s %.2e | %.2e | %.2e" % (n, *errs))
+    den = np.abs(gr["c2w"]).max()
+    print("  c2w", [float(np.abs(res[k]["c2w"] - gr["c2w"]).max() / den) for k in ("simt", "tc+simt", "tc+tc")])
