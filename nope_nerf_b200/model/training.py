@@ -25,6 +25,79 @@ from .common import arange_pixels
 logger_py = logging.getLogger(__name__)
 
 
+class _FlatAdam:
+    """torch.optim.Adam.step() for an optimizer whose parameters alias one flat buffer (or are few, small
+    tensors), executed by nnb_adam_step.  The optimizer object stays the caller's (train.py:58,99,117):
+    hyper-parameters are read from `param_groups` every step (LR schedulers keep working) and the moments live
+    in `optimizer.state[p]` with torch's own keys ('step', 'exp_avg', 'exp_avg_sq'), so `state_dict()` /
+    `load_state_dict()` round-trip with the reference's CheckpointIO unchanged."""
+
+    def __init__(self, optimizer, flat_param=None, flat_slices=None):
+        self.opt = optimizer
+        self.flat_param = flat_param          # callable -> flat tensor aliasing all params (MLP) or None
+        self.flat_slices = flat_slices
+        self.m = self.v = None
+        self.ok = self._supported()
+
+    def _supported(self):
+        o = self.opt
+        if type(o) is not torch.optim.Adam or len(o.param_groups) != 1:
+            return False
+        g = o.param_groups[0]
+        return not (g.get('amsgrad', False) or g.get('maximize', False) or g.get('weight_decay', 0) != 0 or
+                    g.get('capturable', False) or g.get('differentiable', False))
+
+    def _state(self, p, m_view, v_view):
+        st = self.opt.state[p]
+        if 'step' not in st:
+            st['step'] = torch.tensor(0.0, dtype=torch.float32)
+        for key, view in (('exp_avg', m_view), ('exp_avg_sq', v_view)):
+            cur = st.get(key)
+            if cur is None:
+                view.zero_()
+            elif cur.data_ptr() != view.data_ptr():          # e.g. after load_state_dict: adopt the loaded moments
+                view.copy_(cur.to(view.device, view.dtype))
+            st[key] = view
+        return st
+
+    def step(self):
+        g = self.opt.param_groups[0]
+        params = [p for p in g['params'] if p.requires_grad and p.grad is not None]
+        if not self.ok or not params:
+            return self.opt.step()
+        lr, (b1, b2), eps = g['lr'], g['betas'], g['eps']
+        if self.flat_param is not None:
+            flat = self.flat_param()
+            plist = list(g['params'])
+            if len(plist) != len(self.flat_slices) or any(p.data_ptr() != flat.data_ptr() + 4 * o
+                                                          for p, (o, n, s) in zip(plist, self.flat_slices)):
+                return self.opt.step()
+            g0 = plist[0].grad
+            n = flat.numel()
+            if self.m is None or self.m.device != flat.device:
+                self.m = torch.zeros(n, device=flat.device); self.v = torch.zeros(n, device=flat.device)
+            sts = [self._state(p, self.m[o:o + k].view(sh), self.v[o:o + k].view(sh)) for p, (o, k, sh) in zip(plist, self.flat_slices)]
+            step = int(sts[0]['step']) + 1
+            gflat_ptr_ok = all(p.grad is not None and p.grad.data_ptr() == g0.data_ptr() + 4 * o for p, (o, k, sh) in zip(plist, self.flat_slices))
+            if not gflat_ptr_ok:
+                return self.opt.step()
+            gflat = torch.as_strided(g0, (n,), (1,))      # the installed .grad views alias one flat gradient buffer
+            ops.adam_step(flat, gflat, self.m, self.v, step, lr, b1, b2, eps)
+            for st in sts: st['step'] += 1
+        else:
+            if self.m is None:
+                self.m = {}; self.v = {}
+            for p in params:
+                key = id(p)
+                if key not in self.m or self.m[key].shape != p.shape or self.m[key].device != p.device:
+                    self.m[key] = torch.zeros_like(p); self.v[key] = torch.zeros_like(p)
+                st = self._state(p, self.m[key], self.v[key])
+                step = int(st['step']) + 1
+                gr = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                ops.adam_step(p.data, gr, self.m[key], self.v[key], step, lr, b1, b2, eps)
+                st['step'] += 1
+
+
 def _host_diag_check(camera_mat):
     """camera_mat must be diag(kx, ky, -1, 1) (dataset.py:101-104); checked on host tensors only."""
     if camera_mat.is_cuda:
@@ -79,6 +152,9 @@ class Trainer(object):
             self.rank = torch.distributed.get_rank(self.dp_group)
         self._gbuf = None
         self._pix_cache = {}
+        # fused flat-buffer Adam; optimizers remain the caller's objects
+        self.fused_adam = kwargs.get('fused_adam', True)
+        self._fadam = {}
 
     # ------------------------------------------------------------------------------------
     def _grad_buffer(self):
@@ -114,11 +190,25 @@ class Trainer(object):
         if self.distortion_net: self.distortion_net.train()
         loss_dict = self.compute_loss(data, it=it, epoch=epoch, scheduling_start=scheduling_start,
                                       out_render_path=render_path, backward=True)
-        self.optimizer.step()
-        if self.optimizer_pose: self.optimizer_pose.step()
+        self._opt_step(self.optimizer, mlp=True)
+        if self.optimizer_pose: self._opt_step(self.optimizer_pose)
         if self.optimizer_focal: self.optimizer_focal.step()
-        if self.optimizer_distortion: self.optimizer_distortion.step()
+        if self.optimizer_distortion: self._opt_step(self.optimizer_distortion)
         return loss_dict
+
+    def _opt_step(self, opt, mlp=False):
+        if not self.fused_adam:
+            return opt.step()
+        fa = self._fadam.get(id(opt))
+        if fa is None:
+            if mlp:
+                from .official_nerf import PARAM_SLICES
+                net = self.model.renderer.model
+                fa = _FlatAdam(opt, flat_param=net.flat_weights, flat_slices=PARAM_SLICES)
+            else:
+                fa = _FlatAdam(opt)
+            self._fadam[id(opt)] = fa
+        fa.step()
 
     # ------------------------------------------------------------------------------------
     def process_data_dict(self, data):
