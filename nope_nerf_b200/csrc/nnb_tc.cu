@@ -43,7 +43,8 @@ constexpr int SM_AHI = 0, SM_ALO = 65536, SM_EHI = 131072, SM_ELO = 147456, SM_W
 constexpr int SM_BIAS = SM_W + NST * STAGE_BYTES;             // 212992
 constexpr int BIAS_FLOATS = 8 * 256 + 256 + 256 + 384 + 4;    // trunk, feat, w_sigma, W_rgb, (b_sigma, b_rgb[3])
 constexpr int SM_RAYB = SM_BIAS + ((BIAS_FLOATS * 4 + 127) / 128) * 128;
-constexpr int SM_BAR = SM_RAYB + (4 * 128 + 4 * 32) * 4;   // per-ray bias [4][128] + direction-encoding staging [4][32]
+constexpr int SM_PART = SM_RAYB + (4 * 128 + 4 * 32) * 4;   // per-ray bias [4][128] + direction-encoding staging [4][32]
+constexpr int SM_BAR = SM_PART + 128 * 4 * 4;                // head partial sums / exchange buffer
 constexpr int SM_TOTAL = SM_BAR + 32 * 8 + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 enum { B_FULL = 0, B_EMPTY = NST, B_AREADY = 2 * NST, B_EREADY = 2 * NST + 4, B_ACCFULL = 2 * NST + 5, B_ACCEMPTY = 2 * NST + 7, B_COUNT = 2 * NST + 9 };
@@ -81,7 +82,7 @@ __device__ __forceinline__ void row_geometry_tc(const nnb_render_args& a, size_t
   sample_point(a, ray, z, p);
 }
 
-__global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const unsigned char* __restrict__ wimg, SampleRec* __restrict__ recs,
+__global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const unsigned char* __restrict__ wimg, SampleRec* __restrict__ recs,
                                                         TcStash st, size_t M, int n_tiles, int stash) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(B_AREADY + i), 128);
-    mbar_init(BAR(B_EREADY), 128);
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 128); }
+    mbar_init(BAR(B_EREADY), 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (two 256-column fp32 accumulators)
@@ -186,37 +187,63 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
     }
   } else {
     // =============================== epilogue warps ================================
+    // 8 warps: two per TMEM lane quarter.  Thread = sample row; `half` selects which column chunks of the
+    // accumulator this thread converts (two warps per scheduler hide the tcgen05.ld / convert latencies).
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;          // 0: warps 2-5, 1: warps 6-9
     const int row = q * 32 + lane;             // sample row of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     unsigned char* A_hi = smem + SM_AHI; unsigned char* A_lo = smem + SM_ALO;
+    float* s_part = reinterpret_cast<float*>(smem + SM_PART);   // [128][4] head partial sums of half 1
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
       const size_t m = (size_t)tile * TILE + row;
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogues are done with s_rayb
+      epi_bar();   // previous tile's epilogues are done with s_rayb / s_part
       // ---- prologue: geometry, positional encoding -> E operand, per-ray direction bias ----
       Ray ray; int n, i; float z, p[3];
       row_geometry_tc(a, m, M, ray, n, i, z, p);
       {
-        float e[64];
-        encode<10>(p, [&](int k, float v) { e[k] = v; });
-        e[63] = 0.f;
+        // half 0 encodes the raw coordinates + levels 0..4 (E columns 0..32), half 1 levels 5..9 (columns 33..62);
+        // ee[j] holds column 32*half + j.  k-block 4 (columns 32..39) needs column 32 from half 0 -> one exchange.
+        float ee[33];
+        float* s_x = s_part;   // exchange buffer (free until the heads are reduced at the end of the tile)
+        if (half == 0) {
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb)
-          split_store8(e + kb * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
-        if (stash && !st.tcb) {
+          for (int c = 0; c < 3; ++c) ee[c] = p[c];
 #pragma unroll
-          for (int k4 = 0; k4 < 16; ++k4)
-            *reinterpret_cast<float4*>(st.enc + m * 64 + k4 * 4) = make_float4(e[4 * k4], e[4 * k4 + 1], e[4 * k4 + 2], e[4 * k4 + 3]);
+          for (int l = 0; l < 5; ++l) {
+            const float f = (float)(1 << l);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { float sn, cs; sincosf(__fmul_rn(f, p[c]), &sn, &cs); ee[3 + 6 * l + c] = sn; ee[6 + 6 * l + c] = cs; }
+          }
+          s_x[row] = ee[32];
+        } else {
+          ee[31] = 0.f; ee[32] = 0.f;
+#pragma unroll
+          for (int l = 0; l < 5; ++l) {
+            const float f = (float)(32 << l);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { float sn, cs; sincosf(__fmul_rn(f, p[c]), &sn, &cs); ee[1 + 6 * l + c] = sn; ee[4 + 6 * l + c] = cs; }
+          }
         }
-        if (stash && st.tcb) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
-          unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + row * 16;
+        epi_bar();
+        if (half == 1) ee[0] = s_x[row];
 #pragma unroll
-          for (int kb = 0; kb < 8; ++kb) split_store8_bf16(e + kb * 8, dst + kb * 2048, dst + 16384 + kb * 2048);
+        for (int kk = 0; kk < 4; ++kk) {
+          const int kb = half * 4 + kk;
+          split_store8(ee + kk * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
+          if (stash && !st.tcb) {
+            *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8) = make_float4(ee[kk * 8], ee[kk * 8 + 1], ee[kk * 8 + 2], ee[kk * 8 + 3]);
+            *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8 + 4) = make_float4(ee[kk * 8 + 4], ee[kk * 8 + 5], ee[kk * 8 + 6], ee[kk * 8 + 7]);
+          }
+          if (stash && st.tcb) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
+            unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + row * 16;
+            split_store8_bf16(ee + kk * 8, dst + kb * 2048, dst + 16384 + kb * 2048);
+          }
         }
       }
       const int ray_local = (a.S >= TILE) ? 0 : row / a.S;
-      {
+      if (half == 0) {
         // direction-encoding term of rgb_layers.0 is constant per ray: fold it into a per-ray bias
         float v[3], de[32];
         view_dir(a, ray, v);
@@ -229,16 +256,13 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
             *reinterpret_cast<float4*>(st.denc + m * 32 + k4 * 4) = make_float4(de[4 * k4], de[4 * k4 + 1], de[4 * k4 + 2], de[4 * k4 + 3]);
         }
         const bool first_of_ray = (a.S >= TILE) ? (row == 0) : (row % a.S == 0);
-        __syncwarp();
-        // rows that start a ray publish their direction encoding; then 128 threads cooperate
-        float* de_s = s_rayb;  // reuse: first 4*32 floats hold denc per local ray (then overwritten by the bias)
-        if (first_of_ray) {
+        if (first_of_ray) {   // rows that start a ray publish their direction encoding
 #pragma unroll
-          for (int k = 0; k < 32; ++k) de_s[512 + ray_local * 32 + k] = de[k];
+          for (int k = 0; k < 32; ++k) s_rayb[512 + ray_local * 32 + k] = de[k];
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      {
+      epi_bar();
+      if (half == 1) {
         const int nrays = (a.S >= TILE) ? 1 : TILE / a.S;
         const float* w = a.weights;
         for (int r = 0; r < nrays; ++r) {
@@ -250,7 +274,7 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
       }
       fence_async_smem();
       mbar_arrive(BAR(B_EREADY));
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      epi_bar();
       float s_logit = 0.f, c_acc[3] = {0.f, 0.f, 0.f};
       // ---- per-GEMM epilogues ----
       for (int g = 0; g < N_GEMM; ++g) {
@@ -258,12 +282,13 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         const uint32_t use = (uint32_t)t * 5u + (uint32_t)(g >> 1);
         mbar_wait(BAR(B_ACCFULL + buf), use & 1u);
         tc_fence_after();
-        const int nchunks = (g == 9) ? 4 : 8;
+        const int nch = (g == 9) ? 2 : 4;                 // chunks of 32 columns handled by this half
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
         const bool planes = stash && st.tcb;
         unsigned char* xplane = (planes && g < 9) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + row * 16 : nullptr;
 #pragma unroll 1
-        for (int cb = 0; cb < nchunks; ++cb) {
+        for (int ci = 0; ci < nch; ++ci) {
+          const int cb = half * nch + ci;
           uint32_t r[32];
           tc_ld32(lane_addr + buf * 256 + cb * 32, r);
           float v[32];
@@ -307,7 +332,7 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
               const int kblock = cb * 4 + kb;
               split_store8(v + kb * 8, A_hi + kblock * 2048 + row * 16, A_lo + kblock * 2048 + row * 16);
             }
-            if (cb & 1) {  // a 64-column block of the next layer's A operand is complete
+            if (cb & 1) {  // a 64-column block of the next layer's A operand is complete (128 arrivals: this half's 4 warps)
               fence_async_smem();
               mbar_arrive(BAR(B_AREADY + (cb >> 1)));
             }
@@ -316,12 +341,18 @@ __global__ void __launch_bounds__(192, 1) tc_field_fwd(nnb_render_args a, const 
         tc_fence_before();
         mbar_arrive(BAR(B_ACCEMPTY + buf));
       }
-      // ---- heads + per-sample record ----
-      {
-        const float s = s_logit + s_bias[2944];
+      // ---- heads + per-sample record (half 1 hands its partial dot products to half 0) ----
+      if (half == 1) {
+        *reinterpret_cast<float4*>(s_part + row * 4) = make_float4(s_logit, c_acc[0], c_acc[1], c_acc[2]);
+      }
+      epi_bar();
+      if (half == 0) {
+        const float4 o = *reinterpret_cast<const float4*>(s_part + row * 4);
+        const float s = s_logit + o.x + s_bias[2944];
         float sigma;
         SampleRec rec;
-        rec.r = sigmoid_f(c_acc[0] + s_bias[2945]); rec.g = sigmoid_f(c_acc[1] + s_bias[2946]); rec.b = sigmoid_f(c_acc[2] + s_bias[2947]);
+        rec.r = sigmoid_f(c_acc[0] + o.y + s_bias[2945]); rec.g = sigmoid_f(c_acc[1] + o.z + s_bias[2946]);
+        rec.b = sigmoid_f(c_acc[2] + o.w + s_bias[2947]);
         rec.a = density_act(s, a.flags, &sigma); rec.s = s; rec.z = z; rec.pad0 = 0.f; rec.pad1 = 0.f;
         recs[m] = rec;
       }
@@ -401,7 +432,7 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
   nnb_prof_mark(st);
   const int n_tiles = (int)((L.M + TILE - 1) / TILE);
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  tc_field_fwd<<<grid, 192, SM_TOTAL, st>>>(a, img, recs, ts, L.M, n_tiles, stash);
+  tc_field_fwd<<<grid, 320, SM_TOTAL, st>>>(a, img, recs, ts, L.M, n_tiles, stash);
   nnb_prof_mark(st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -93,7 +93,7 @@ __device__ __forceinline__ void row_geometry_b(const nnb_render_args& a, size_t 
 }
 
 template <bool GBF>
-__global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsigned char* __restrict__ wimg, DgradPtrs P, size_t M,
+__global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsigned char* __restrict__ wimg, DgradPtrs P, size_t M,
                                                     int n_tiles, int write_dy) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(D_AREADY + i), 128);
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(D_ACCFULL + i), 1); mbar_init(BAR(D_ACCEMPTY + i), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(D_ACCFULL + i), 1); mbar_init(BAR(D_ACCEMPTY + i), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
       }
     }
   } else {
-    const int q = warp & 3, row = q * 32 + lane;
+    // 8 epilogue warps: two per TMEM lane quarter; `half` selects the column chunks this thread converts
+    const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;
+    const bool leader = (row == 0 && half == 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     unsigned char* A_hi = smem + DG_AHI; unsigned char* A_lo = smem + DG_ALO;
     const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo);
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
       const int tile = blockIdx.x + t * gridDim.x;
       const size_t m = (size_t)tile * TILE + row;
       // ---- prologue: head adjoints -> g_yr (A version 0) ----
-      if (row == 0) bulk_wait_read0();
+      if (leader) bulk_wait_read0();
       epi_bar();
       float g_s;
       {
@@ -191,12 +193,12 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
         SampleRec rec = P.rec[m];
         float gyc0 = g.x * rec.r * (1.f - rec.r), gyc1 = g.y * rec.g * (1.f - rec.g), gyc2 = g.z * rec.b * (1.f - rec.b);
         g_s = g.w * density_act_grad(rec.s, a.flags);
-        P.dyc[m] = make_float4(gyc0, gyc1, gyc2, g_s);          // fp32 side stash stays unscaled
+        if (half == 0) P.dyc[m] = make_float4(gyc0, gyc1, gyc2, g_s);          // fp32 side stash stays unscaled
         gyc0 *= gscale; gyc1 *= gscale; gyc2 *= gscale; g_s *= gscale;
         const float* hr = P.hr + m * 128;
         float* dyr = P.dyr + m * 128;
 #pragma unroll 1
-        for (int jb = 0; jb < 16; ++jb) {
+        for (int jb = half * 8; jb < half * 8 + 8; ++jb) {
           float4 h0 = *reinterpret_cast<const float4*>(hr + jb * 8), h1 = *reinterpret_cast<const float4*>(hr + jb * 8 + 4);
           float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w}, v[8];
 #pragma unroll
@@ -210,10 +212,10 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
         }
       }
       fence_async_smem();
-#pragma unroll
-      for (int b = 0; b < 4; ++b) mbar_arrive(BAR(D_AREADY + b));
+      mbar_arrive(BAR(D_AREADY + half));          // columns 64*half .. of g_yr (128 arrivals per block: this half's 4 warps)
+      mbar_arrive(BAR(D_AREADY + 2 + half));      // blocks 2,3 are empty in A version 0 (K = 128)
       epi_bar();
-      if (row == 0 && write_dy) {   // dY planes of rgb_layers.0 (128 features = first 32 KB of each image)
+      if (leader && write_dy) {   // dY planes of rgb_layers.0 (128 features = first 32 KB of each image)
         unsigned char* dst = P.dyp[9] + (size_t)tile * PLANE_TILE_128;
         bulk_s2g(dst, a_hi_s, 32768); bulk_s2g(dst + 32768, a_lo_s, 32768); bulk_commit();
       }
@@ -224,13 +226,14 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
         mbar_wait(BAR(D_ACCFULL + buf), use & 1u);
         tc_fence_after();
         const bool writes_a = (pos != 5 && pos != 10);
-        if (writes_a) { if (row == 0) bulk_wait_read0(); epi_bar(); }   // previous image fully read by its bulk store
+        if (writes_a) { if (leader) bulk_wait_read0(); epi_bar(); }   // previous image fully read by its bulk store
         // mask layer: g_y_l = g_h_l * (h_l > 0) with l = 7 (pos1), 6,5,4 (pos2..4), 3 (pos6), 2,1,0 (pos7..9)
         const int mask_l = (pos == 1) ? 7 : (pos >= 2 && pos <= 4) ? 8 - pos : (pos == 6) ? 3 : (pos >= 7 && pos <= 9) ? 9 - pos : -1;
         const uint32_t* mrow = (mask_l >= 0) ? P.mask + ((size_t)mask_l * P.Mpad + m) * 8 : nullptr;
-        const int nchunks = (pos == 5 || pos == 10) ? 2 : 8;
+        const int nch = (pos == 5 || pos == 10) ? 1 : 4;   // 32-column chunks handled by this half
 #pragma unroll 1
-        for (int cb = 0; cb < nchunks; ++cb) {
+        for (int ci = 0; ci < nch; ++ci) {
+          const int cb = half * nch + ci;
           uint32_t r[32];
           tc_ld32(lane_addr + buf * 256 + cb * 32, r);
           float v[32];
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
         mbar_arrive(BAR(D_ACCEMPTY + buf));
         if (writes_a) {
           epi_bar();
-          if (row == 0 && write_dy) {
+          if (leader && write_dy) {
             // A now holds: pos0 -> g_feat ; pos1 -> g_y7 ; pos2..4 -> g_y6..4 ; pos6 -> g_y3 ; pos7..9 -> g_y2..0
             const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
             unsigned char* dst = P.dyp[di] + (size_t)tile * PLANE_TILE_256;
@@ -266,15 +269,16 @@ __global__ void __launch_bounds__(192, 1) tc_dgrad(nnb_render_args a, const unsi
           }
         }
       }
-      // ---- encoding adjoint ----
-      {
+      // ---- encoding adjoint (both halves' columns of g_enc are in shared memory) ----
+      epi_bar();
+      if (half == 0) {
         Ray ray; int n, i; float z, p[3], gp[3];
         row_geometry_b(a, m, M, ray, n, i, z, p);
         encode_bwd<10>(p, [&](int k) { return s_genc[k * 128 + row]; }, gp);
         P.gp[m] = make_float4(gp[0] * inv_gscale, gp[1] * inv_gscale, gp[2] * inv_gscale, 0.f);
       }
     }
-    if (row == 0) bulk_wait0();
+    if (leader) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -439,15 +443,37 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
 }
 
 // per-ray view-direction gradient from the rgb hidden layer: g_v = encode_bwd( (sum_i g_yr_i) @ W_r[:,256:283] )
-__global__ void ray_dir_grad(nnb_render_args a, const float* __restrict__ dyr, float4* __restrict__ gv) {
+// The direction encoding is constant along a ray, so both the per-ray view-direction gradient and the weight
+// gradient of rgb_layers.0[:, 256:283] only need G_ray[j] = sum_i g_yr[i][j]:
+//   dW[j][256+k] += G_ray[j] * denc_ray[k]   (block-reduced in shared memory, then one atomic per element)
+__global__ void ray_dir_grad(nnb_render_args a, const float* __restrict__ dyr, const float* __restrict__ denc, float4* __restrict__ gv,
+                             float* __restrict__ g_wdir /* gflat + W_RGBH + 256, row stride 283, or NULL */) {
+  __shared__ float s_dw[128 * 27];
+  for (int i = threadIdx.x; i < 128 * 27; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
   const int lane = threadIdx.x & 31, n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= a.N) return;
+  const bool active = n < a.N;
   float G[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int i = 0; i < a.S; ++i) {
-    const float* r = dyr + ((size_t)n * a.S + i) * 128;
+  if (active) {
+    for (int i = 0; i < a.S; ++i) {
+      const float* r = dyr + ((size_t)n * a.S + i) * 128;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) G[q] += r[lane + 32 * q];
+      for (int q = 0; q < 4; ++q) G[q] += r[lane + 32 * q];
+    }
+    if (g_wdir) {
+      const float* de = denc + (size_t)n * a.S * 32;
+#pragma unroll 1
+      for (int k = 0; k < 27; ++k) {
+        const float dk = __ldg(de + k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicAdd(&s_dw[(lane + 32 * q) * 27 + k], G[q] * dk);
+      }
+    }
   }
+  __syncthreads();
+  if (g_wdir)
+    for (int i = threadIdx.x; i < 128 * 27; i += blockDim.x) atomicAdd(g_wdir + (size_t)(i / 27) * 283 + (i % 27), s_dw[i]);
+  if (!active) return;
   float gd[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) {
@@ -465,6 +491,31 @@ __global__ void ray_dir_grad(nnb_render_args a, const float* __restrict__ dyr, f
     out = make_float4(g[0], g[1], g[2], 0.f);
   }
   for (int i = lane; i < a.S; i += 32) gv[(size_t)n * a.S + i] = (i == 0) ? out : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// fc_density (1 x 256) and fc_rgb (3 x 128) weight / bias gradients: memory-bound streaming reductions over
+// the fp32 side stashes h7 [M][256], hr [M][128], dyc [M][4] = (g_yc0, g_yc1, g_yc2, g_s)
+__global__ void __launch_bounds__(256) head_wgrad(const float4* __restrict__ dyc, const float* __restrict__ h7, const float* __restrict__ hr,
+                                                   size_t M, int chunk, float* __restrict__ gflat) {
+  const size_t m0 = (size_t)blockIdx.x * chunk, m1 = m0 + chunk < M ? m0 + chunk : M;
+  const int t = threadIdx.x, j = t & 127, par = t >> 7;
+  float ad = 0.f, ac[3] = {0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  for (size_t m = m0; m < m1; ++m) {
+    const float4 g = __ldg(dyc + m);
+    ad = fmaf(g.w, __ldg(h7 + m * 256 + t), ad);
+    if (((m - m0) & 1) == (size_t)par) {
+      const float h = __ldg(hr + m * 128 + j);
+      ac[0] = fmaf(g.x, h, ac[0]); ac[1] = fmaf(g.y, h, ac[1]); ac[2] = fmaf(g.z, h, ac[2]);
+    }
+    if (t == 0) { ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w; }
+  }
+  atomicAdd(gflat + nnb::W_SIG + t, ad);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) atomicAdd(gflat + nnb::W_RGB + c * 128 + j, ac[c]);
+  if (t == 0) {
+    atomicAdd(gflat + nnb::B_RGB + 0, ab[0]); atomicAdd(gflat + nnb::B_RGB + 1, ab[1]); atomicAdd(gflat + nnb::B_RGB + 2, ab[2]);
+    atomicAdd(gflat + nnb::B_SIG, ab[3]);
+  }
 }
 
 bool g_table_t_ready = false;
@@ -531,7 +582,7 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   const int n_tiles = (int)L.n_tiles;
   const int write_dy = b.g_weights ? 1 : 0;
   const int grid_d = n_tiles < n_sm ? n_tiles : n_sm;
-  tc_dgrad<true><<<grid_d, 192, DG_TOTAL, st>>>(a, img_t, P, L.M, n_tiles, write_dy);
+  tc_dgrad<true><<<grid_d, 320, DG_TOTAL, st>>>(a, img_t, P, L.M, n_tiles, write_dy);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
@@ -559,18 +610,18 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
     tc_wgrad<true><<<nj * msplit, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    SmallJob sj[3];
-    const float* dyc = reinterpret_cast<const float*>(base + L.dyc);
-    const float* h7 = reinterpret_cast<const float*>(base + L.h[7]);
-    sj[0] = SmallJob{dyc + 3, h7, b.g_weights + nnb::W_SIG, b.g_weights + nnb::B_SIG, 4, 1, 256, 256, 256};
-    sj[1] = SmallJob{dyc, reinterpret_cast<const float*>(base + L.hr), b.g_weights + nnb::W_RGB, b.g_weights + nnb::B_RGB, 4, 3, 128, 128, 128};
-    sj[2] = SmallJob{reinterpret_cast<const float*>(base + L.dyr), reinterpret_cast<const float*>(base + L.denc),
-                     b.g_weights + nnb::W_RGBH + 256, nullptr, 128, 128, 32, 27, 283};
-    e = launch_simt_wgrad_jobs(sj, 3, L.M, st);
+    {  // small heads: fc_density / fc_rgb (streaming reduction); the direction slice of rgb_layers.0 rides on ray_dir_grad
+      const int chunk = 256;
+      head_wgrad<<<(unsigned)((L.M + chunk - 1) / chunk), 256, 0, st>>>(reinterpret_cast<const float4*>(base + L.dyc),
+                                                                         reinterpret_cast<const float*>(base + L.h[7]),
+                                                                         reinterpret_cast<const float*>(base + L.hr), L.M, chunk, b.g_weights);
+      e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return e;
   }
   nnb_prof_mark(st);
-  ray_dir_grad<<<(a.N + 7) / 8, 256, 0, st>>>(a, reinterpret_cast<const float*>(base + L.dyr), gv);
+  ray_dir_grad<<<(a.N + 7) / 8, 256, 0, st>>>(a, reinterpret_cast<const float*>(base + L.dyr), reinterpret_cast<const float*>(base + L.denc), gv,
+                                              b.g_weights ? b.g_weights + nnb::W_RGBH + 256 : nullptr);
   e = launch_ray_bwd(b, recs, gp, gv, st);
   nnb_prof_mark(st);
   return e;

@@ -21,11 +21,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
+      ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware instead of spinning
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -79,16 +79,15 @@ __device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_d
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-    float r0 = v[2 * i] - __half2float(h0), r1 = v[2 * i + 1] - __half2float(h1);
-    __half2 hh = __halves2half2(h0, h1);
+    __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);        // one F2FP per pair
+    float2 hf = __half22float2(hh);
+    __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
     hi[i] = *reinterpret_cast<uint32_t*>(&hh);
-    lo[i] = pack_half2(r0, r1);
+    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
   }
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
-
 
 // bf16 hi/lo split (x = hi + lo to ~2^-17, full fp32 exponent range): used for GRADIENT operands, whose
 // magnitudes decay by orders of magnitude along the backward chain (fp16 would run into subnormals)
@@ -96,11 +95,11 @@ __device__ __forceinline__ void split_store8_bf16(const float* v, unsigned char*
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    float r0 = v[2 * i] - __bfloat162float(h0), r1 = v[2 * i + 1] - __bfloat162float(h1);
-    __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
-    __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
-    hi[i] = *reinterpret_cast<uint32_t*>(&hh);
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<uint32_t*>(&hh);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);   // bf16 -> f32 is a shift
+    __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+    hi[i] = hb;
     lo[i] = *reinterpret_cast<uint32_t*>(&ll);
   }
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -122,5 +121,5 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 }  // namespace tcu
