@@ -20,6 +20,7 @@
 // operand lives at byte  (k/8) * rows*16 + row*16 + (k%8)*2 : 8x8 core matrices of 128 contiguous
 // bytes, SBO = 128 B between row-groups, LBO = rows*16 B between the two k-halves of one MMA.
 #include "nnb_tc_common.cuh"
+#include <cstdlib>
 
 cudaError_t launch_composite_fwd(const nnb_render_args& a, const SampleRec* recs, cudaStream_t st);
 cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
@@ -82,6 +83,7 @@ __device__ __forceinline__ void row_geometry_tc(const nnb_render_args& a, size_t
   sample_point(a, ray, z, p);
 }
 
+template <int CL>   // CL = thread-block cluster size (1 | 2 | 4): CTAs of a cluster share every weight stage via multicast
 __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const unsigned char* __restrict__ wimg, SampleRec* __restrict__ recs,
                                                         TcStash st, size_t M, int n_tiles, int stash) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), CL); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(B_AREADY + i), 128);
     mbar_init(BAR(B_EREADY), 256);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 256); }
@@ -119,9 +121,14 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();    // every CTA's barriers are initialised before any remote arrive / multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // all CTAs run the same number of tile iterations (the weight stream is shared inside a cluster);
+  // iterations whose tile index is past the end only keep the stream flowing
+  const int my_tiles = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     // =============================== weight producer ===============================
@@ -130,9 +137,14 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
       for (int t = 0; t < my_tiles; ++t) {
         for (int s = 0; s < N_STAGES; ++s) {
           const int bytes = c_stages[s].nrows * 64;
-          mbar_wait(BAR(B_EMPTY + slot), phase ^ 1);
+          mbar_wait(BAR(B_EMPTY + slot), phase ^ 1);          // all CL consumers released this slot
           mbar_expect_tx(BAR(B_FULL + slot), bytes);
-          bulk_g2s(smem_u32(smem + SM_W + slot * STAGE_BYTES), wimg + c_stages[s].img_off, bytes, BAR(B_FULL + slot));
+          if (CL == 1) bulk_g2s(smem_u32(smem + SM_W + slot * STAGE_BYTES), wimg + c_stages[s].img_off, bytes, BAR(B_FULL + slot));
+          else {   // this CTA fetches slice `crank` of the stage and multicasts it into every CTA of the cluster
+            const int sl = bytes / CL;
+            bulk_g2s_mc(smem_u32(smem + SM_W + slot * STAGE_BYTES + crank * sl), wimg + c_stages[s].img_off + crank * sl, sl,
+                        BAR(B_FULL + slot), cmask);
+          }
           if (++slot == NST) { slot = 0; phase ^= 1; }
         }
       }
@@ -143,10 +155,20 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
       uint32_t slot = 0, phase = 0;
       const uint32_t a_hi = smem_u32(smem + SM_AHI), a_lo = smem_u32(smem + SM_ALO);
       const uint32_t e_hi = smem_u32(smem + SM_EHI), e_lo = smem_u32(smem + SM_ELO);
+      int tv = 0;   // number of VALID tiles processed so far (phase bookkeeping of the per-tile barriers)
       for (int t = 0; t < my_tiles; ++t) {
+        if (blockIdx.x + t * gridDim.x >= n_tiles) {   // past the end: consume + release the stages only
+          for (int s = 0; s < N_STAGES; ++s) {
+            mbar_wait(BAR(B_FULL + slot), phase);
+            tc_fence_after();
+            if (CL == 1) tc_commit(BAR(B_EMPTY + slot)); else tc_commit_mc(BAR(B_EMPTY + slot), cmask);
+            if (++slot == NST) { slot = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int g = 0; g < N_GEMM; ++g) {
           const int buf = g & 1;
-          const uint32_t use = (uint32_t)t * 5u + (uint32_t)(g >> 1);
+          const uint32_t use = (uint32_t)tv * 5u + (uint32_t)(g >> 1);
           mbar_wait(BAR(B_ACCEMPTY + buf), (use & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * 256;
@@ -155,7 +177,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           const uint32_t b_lbo = N * 16;
           const int e_steps = (g == 0 || g == 4) ? 4 : 0;
           const int a_steps = (g == 0) ? 0 : 16;
-          if (e_steps) { if (g == 0) { mbar_wait(BAR(B_EREADY), (uint32_t)t & 1u); tc_fence_after(); } }
+          if (e_steps) { if (g == 0) { mbar_wait(BAR(B_EREADY), (uint32_t)tv & 1u); tc_fence_after(); } }
           uint32_t acc = 0;
           for (int ks = 0; ks < e_steps + a_steps; ++ks) {
             uint32_t ahi, alo;
@@ -163,7 +185,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             else {
               const int ka = ks - e_steps;
               if ((ka & 3) == 0) {  // first k-step of a 64-column block: wait for the previous epilogue
-                const uint32_t au = (uint32_t)t * 9u + (uint32_t)(g - 1);
+                const uint32_t au = (uint32_t)tv * 9u + (uint32_t)(g - 1);
                 mbar_wait(BAR(B_AREADY + (ka >> 2)), au & 1u);
                 tc_fence_after();
               }
@@ -178,11 +200,12 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             tc_mma_f16(d_tmem, dAh, dBl, idesc, 1u);
             tc_mma_f16(d_tmem, dAh, dBh, idesc, 1u);
             acc = 1u;
-            tc_commit(BAR(B_EMPTY + slot));
+            if (CL == 1) tc_commit(BAR(B_EMPTY + slot)); else tc_commit_mc(BAR(B_EMPTY + slot), cmask);
             if (++slot == NST) { slot = 0; phase ^= 1; }
           }
           tc_commit(BAR(B_ACCFULL + buf));
         }
+        ++tv;
       }
     }
   } else {
@@ -195,8 +218,11 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     unsigned char* A_hi = smem + SM_AHI; unsigned char* A_lo = smem + SM_ALO;
     float* s_part = reinterpret_cast<float*>(smem + SM_PART);   // [128][4] head partial sums of half 1
-    for (int t = 0; t < my_tiles; ++t) {
-      const int tile = blockIdx.x + t * gridDim.x;
+    int tv = -1;
+    for (int tt = 0; tt < my_tiles; ++tt) {
+      const int tile = blockIdx.x + tt * gridDim.x;
+      if (tile >= n_tiles) continue;
+      const int t = ++tv;        // index among this CTA's valid tiles (barrier phase bookkeeping)
       const size_t m = (size_t)tile * TILE + row;
       epi_bar();   // previous tile's epilogues are done with s_rayb / s_part
       // ---- prologue: geometry, positional encoding -> E operand, per-ray direction bias ----
@@ -360,6 +386,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();    // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -406,7 +433,11 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
   static bool attr = false;
   static int n_sm = 0;
   if (!attr) {
-    e = cudaFuncSetAttribute(tc_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    e = cudaFuncSetAttribute(tc_field_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_field_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_field_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (e != cudaSuccess) return e;
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -431,10 +462,13 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
   tc_prep_weights<<<N_STAGES, 256, 0, st>>>(a.weights, img);
   nnb_prof_mark(st);
   const int n_tiles = (int)((L.M + TILE - 1) / TILE);
-  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  tc_field_fwd<<<grid, 320, SM_TOTAL, st>>>(a, img, recs, ts, L.M, n_tiles, stash);
+  const int CL = cluster_size_option();
+  int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  grid = (grid + CL - 1) / CL * CL; if (grid > n_sm) grid = n_sm / CL * CL;
+  if (CL == 4) e = launch_clustered(tc_field_fwd<4>, grid, 320, SM_TOTAL, 4, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
+  else if (CL == 2) e = launch_clustered(tc_field_fwd<2>, grid, 320, SM_TOTAL, 2, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
+  else e = launch_clustered(tc_field_fwd<1>, grid, 320, SM_TOTAL, 1, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
   nnb_prof_mark(st);
-  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   e = launch_composite_fwd(a, recs, st);
   nnb_prof_mark(st);

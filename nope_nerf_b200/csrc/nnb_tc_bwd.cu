@@ -92,7 +92,7 @@ __device__ __forceinline__ void row_geometry_b(const nnb_render_args& a, size_t 
   sample_point(a, ray, z, p);
 }
 
-template <bool GBF>
+template <bool GBF, int CL>
 __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsigned char* __restrict__ wimg, DgradPtrs P, size_t M,
                                                     int n_tiles, int write_dy) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), CL); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(D_AREADY + i), 128);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(D_ACCFULL + i), 1); mbar_init(BAR(D_ACCEMPTY + i), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -117,9 +117,12 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
     s_small[i] = (i < 384) ? __ldg(a.weights + nnb::W_RGB + i) : __ldg(a.weights + nnb::W_SIG + (i - 384));
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_tiles = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;    // uniform across the cluster (shared weight stream)
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   const float gscale = GBF ? 1.f : grad_scale_from(P.gmax), inv_gscale = 1.f / gscale;
   auto split_g = [&](const float* v, unsigned char* hi, unsigned char* lo) {
     if (GBF) split_store8_bf16(v, hi, lo); else split_store8(v, hi, lo);
@@ -133,7 +136,12 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           const int bytes = c_stages_t[s].nrows * 64;
           mbar_wait(BAR(D_EMPTY + slot), phase ^ 1);
           mbar_expect_tx(BAR(D_FULL + slot), bytes);
-          bulk_g2s(smem_u32(smem + DG_W + slot * STAGE_BYTES), wimg + c_stages_t[s].img_off, bytes, BAR(D_FULL + slot));
+          if (CL == 1) bulk_g2s(smem_u32(smem + DG_W + slot * STAGE_BYTES), wimg + c_stages_t[s].img_off, bytes, BAR(D_FULL + slot));
+          else {
+            const int sl = bytes / CL;
+            bulk_g2s_mc(smem_u32(smem + DG_W + slot * STAGE_BYTES + crank * sl), wimg + c_stages_t[s].img_off + crank * sl, sl,
+                        BAR(D_FULL + slot), cmask);
+          }
           if (++slot == NST) { slot = 0; phase ^= 1; }
         }
     }
@@ -141,7 +149,18 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
       const uint32_t a_hi = smem_u32(smem + DG_AHI), a_lo = smem_u32(smem + DG_ALO);
-      for (int t = 0; t < my_tiles; ++t) {
+      int tv = 0;
+      for (int tt = 0; tt < my_tiles; ++tt) {
+        if (blockIdx.x + tt * gridDim.x >= n_tiles) {   // past the end: keep the shared weight stream flowing
+          for (int s = 0; s < N_STAGES_T; ++s) {
+            mbar_wait(BAR(D_FULL + slot), phase);
+            tc_fence_after();
+            if (CL == 1) tc_commit(BAR(D_EMPTY + slot)); else tc_commit_mc(BAR(D_EMPTY + slot), cmask);
+            if (++slot == NST) { slot = 0; phase ^= 1; }
+          }
+          continue;
+        }
+        const int t = tv++;
         for (int pos = 0; pos < N_POS; ++pos) {
           const int buf = pos & 1;
           const uint32_t use = buf ? (uint32_t)t * 5u + (uint32_t)(pos >> 1) : (uint32_t)t * 6u + (uint32_t)(pos >> 1);
@@ -167,7 +186,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
             tc_mma_f16(d_tmem, dAh, dBl, idesc, 1u);
             tc_mma_f16(d_tmem, dAh, dBh, idesc, 1u);
             acc = 1u;
-            tc_commit(BAR(D_EMPTY + slot));
+            if (CL == 1) tc_commit(BAR(D_EMPTY + slot)); else tc_commit_mc(BAR(D_EMPTY + slot), cmask);
             if (++slot == NST) { slot = 0; phase ^= 1; }
           }
           tc_commit(BAR(D_ACCFULL + buf));
@@ -181,8 +200,11 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     unsigned char* A_hi = smem + DG_AHI; unsigned char* A_lo = smem + DG_ALO;
     const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo);
-    for (int t = 0; t < my_tiles; ++t) {
-      const int tile = blockIdx.x + t * gridDim.x;
+    int tv = -1;
+    for (int tt = 0; tt < my_tiles; ++tt) {
+      const int tile = blockIdx.x + tt * gridDim.x;
+      if (tile >= n_tiles) continue;
+      const int t = ++tv;
       const size_t m = (size_t)tile * TILE + row;
       // ---- prologue: head adjoints -> g_yr (A version 0) ----
       if (leader) bulk_wait_read0();
@@ -282,6 +304,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -551,7 +574,11 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   static bool attr = false;
   static int n_sm = 0;
   if (!attr) {
-    e = cudaFuncSetAttribute(tc_dgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL);
+    e = cudaFuncSetAttribute(tc_dgrad<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_dgrad<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_dgrad<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_TOTAL);
     if (e != cudaSuccess) return e;
@@ -581,9 +608,12 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   P.Mpad = L.Mpad; P.gmax = gmax;
   const int n_tiles = (int)L.n_tiles;
   const int write_dy = b.g_weights ? 1 : 0;
-  const int grid_d = n_tiles < n_sm ? n_tiles : n_sm;
-  tc_dgrad<true><<<grid_d, 320, DG_TOTAL, st>>>(a, img_t, P, L.M, n_tiles, write_dy);
-  e = cudaGetLastError();
+  const int CL = cluster_size_option();
+  int grid_d = n_tiles < n_sm ? n_tiles : n_sm;
+  grid_d = (grid_d + CL - 1) / CL * CL; if (grid_d > n_sm) grid_d = n_sm / CL * CL;
+  if (CL == 4) e = launch_clustered(tc_dgrad<true, 4>, grid_d, 320, DG_TOTAL, 4, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
+  else if (CL == 2) e = launch_clustered(tc_dgrad<true, 2>, grid_d, 320, DG_TOTAL, 2, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
+  else e = launch_clustered(tc_dgrad<true, 1>, grid_d, 320, DG_TOTAL, 1, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
   if (b.g_weights) {
