@@ -26,7 +26,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("NNB_EXTRA_NVCC_FLAGS", "").split()
     if not os.path.exists(os.path.join(CSRC, "nnb_tc.cu")):
         flags.remove("-DNNB_WITH_TC")
     objs = []

@@ -70,6 +70,16 @@ __global__ void tc_prep_weights(const float* __restrict__ w, unsigned char* __re
   }
 }
 
+#ifdef NNB_TC_PROFILE
+__device__ unsigned long long g_tcprof[148][8];
+__device__ unsigned long long g_tcprof2[148][8];
+#define PROF_T0() unsigned long long _t0 = clock64()
+#define PROF_ADD(slot) do { unsigned long long _t1 = clock64(); _pacc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#endif
+
 struct TcStash {   // fp32 [sample][feature] stash (layout of nnb_simt.cu) and, with NNB_TCBWD, operand planes + ReLU bitmasks
   float *h[8], *feat, *hr, *enc, *denc;
   unsigned char* xp[10]; uint32_t* mask; size_t Mpad; int tcb;
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), CL); }
-    for (int i = 0; i < 4; ++i) mbar_init(BAR(B_AREADY + i), 128);
+    for (int i = 0; i < 4; ++i) mbar_init(BAR(B_AREADY + i), 256);
     mbar_init(BAR(B_EREADY), 256);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -156,6 +166,10 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
       const uint32_t a_hi = smem_u32(smem + SM_AHI), a_lo = smem_u32(smem + SM_ALO);
       const uint32_t e_hi = smem_u32(smem + SM_EHI), e_lo = smem_u32(smem + SM_ELO);
       int tv = 0;   // number of VALID tiles processed so far (phase bookkeeping of the per-tile barriers)
+#ifdef NNB_TC_PROFILE
+      unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const unsigned long long _tstart = clock64();
+#endif
       for (int t = 0; t < my_tiles; ++t) {
         if (blockIdx.x + t * gridDim.x >= n_tiles) {   // past the end: consume + release the stages only
           for (int s = 0; s < N_STAGES; ++s) {
@@ -169,8 +183,10 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         for (int g = 0; g < N_GEMM; ++g) {
           const int buf = g & 1;
           const uint32_t use = (uint32_t)tv * 5u + (uint32_t)(g >> 1);
+          PROF_T0();
           mbar_wait(BAR(B_ACCEMPTY + buf), (use & 1u) ^ 1u);
           tc_fence_after();
+          PROF_ADD(0);
           const uint32_t d_tmem = tmem_base + buf * 256;
           const int N = (g == 9) ? 128 : 256;
           const uint32_t idesc = make_idesc(128, N);
@@ -178,7 +194,9 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           const int e_steps = (g == 0 || g == 4) ? 4 : 0;
           const int a_steps = (g == 0) ? 0 : 16;
           if (e_steps) { if (g == 0) { mbar_wait(BAR(B_EREADY), (uint32_t)tv & 1u); tc_fence_after(); } }
+          PROF_ADD(1);
           uint32_t acc = 0;
+          uint32_t full_ok = mbar_probe(BAR(B_FULL + slot), phase);    // probe early: its latency hides under the other waits
           for (int ks = 0; ks < e_steps + a_steps; ++ks) {
             uint32_t ahi, alo;
             if (ks < e_steps) { ahi = e_hi + ks * 4096; alo = e_lo + ks * 4096; }
@@ -191,8 +209,10 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
               }
               ahi = a_hi + ka * 4096; alo = a_lo + ka * 4096;
             }
-            mbar_wait(BAR(B_FULL + slot), phase);
+            PROF_ADD(2);
+            if (!full_ok) mbar_wait(BAR(B_FULL + slot), phase);
             tc_fence_after();
+            PROF_ADD(3);
             const uint32_t wb = smem_u32(smem + SM_W + slot * STAGE_BYTES);
             const uint64_t dAh = make_desc(ahi, 2048, 128), dAl = make_desc(alo, 2048, 128);
             const uint64_t dBh = make_desc(wb, b_lbo, 128), dBl = make_desc(wb + N * 32, b_lbo, 128);
@@ -200,13 +220,21 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             tc_mma_f16(d_tmem, dAh, dBl, idesc, 1u);
             tc_mma_f16(d_tmem, dAh, dBh, idesc, 1u);
             acc = 1u;
+            {   // probe the NEXT stage's barrier before committing: the round trip overlaps the MMA issue / commit
+              const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
+              full_ok = mbar_probe(BAR(B_FULL + nslot), nphase);
+            }
             if (CL == 1) tc_commit(BAR(B_EMPTY + slot)); else tc_commit_mc(BAR(B_EMPTY + slot), cmask);
             if (++slot == NST) { slot = 0; phase ^= 1; }
+            PROF_ADD(4);
           }
           tc_commit(BAR(B_ACCFULL + buf));
         }
         ++tv;
       }
+#ifdef NNB_TC_PROFILE
+      if (blockIdx.x < 148) { for (int i = 0; i < 5; ++i) g_tcprof[blockIdx.x][i] = _pacc[i]; g_tcprof[blockIdx.x][5] = clock64() - _tstart; g_tcprof[blockIdx.x][6] = tv; }
+#endif
     }
   } else {
     // =============================== epilogue warps ================================
@@ -218,12 +246,16 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     unsigned char* A_hi = smem + SM_AHI; unsigned char* A_lo = smem + SM_ALO;
     float* s_part = reinterpret_cast<float*>(smem + SM_PART);   // [128][4] head partial sums of half 1
+#ifdef NNB_TC_PROFILE
+    unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     int tv = -1;
     for (int tt = 0; tt < my_tiles; ++tt) {
       const int tile = blockIdx.x + tt * gridDim.x;
       if (tile >= n_tiles) continue;
       const int t = ++tv;        // index among this CTA's valid tiles (barrier phase bookkeeping)
       const size_t m = (size_t)tile * TILE + row;
+      PROF_T0();
       epi_bar();   // previous tile's epilogues are done with s_rayb / s_part
       // ---- prologue: geometry, positional encoding -> E operand, per-ray direction bias ----
       Ray ray; int n, i; float z, p[3];
@@ -264,7 +296,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           }
           if (stash && st.tcb) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
             unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + row * 16;
-            split_store8_bf16(ee + kk * 8, dst + kb * 2048, dst + 16384 + kb * 2048);
+            split_stream8_bf16(ee + kk * 8, dst + kb * 2048, dst + 16384 + kb * 2048);
           }
         }
       }
@@ -302,70 +334,95 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
       mbar_arrive(BAR(B_EREADY));
       epi_bar();
       float s_logit = 0.f, c_acc[3] = {0.f, 0.f, 0.f};
+      PROF_ADD(0);
       // ---- per-GEMM epilogues ----
       for (int g = 0; g < N_GEMM; ++g) {
         const int buf = g & 1;
         const uint32_t use = (uint32_t)t * 5u + (uint32_t)(g >> 1);
         mbar_wait(BAR(B_ACCFULL + buf), use & 1u);
         tc_fence_after();
+        PROF_ADD(1);
         const int nch = (g == 9) ? 2 : 4;                 // chunks of 32 columns handled by this half
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
         const bool planes = stash && st.tcb;
         unsigned char* xplane = (planes && g < 9) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + row * 16 : nullptr;
+        // pass 1 (critical path of the MMA warp): accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand, block by block.
+        // The two halves convert adjacent 32-column chunks of the SAME 64-column block, so block `ci` is complete
+        // after one chunk time.
+        if (g < 9) {
 #pragma unroll 1
-        for (int ci = 0; ci < nch; ++ci) {
-          const int cb = half * nch + ci;
-          uint32_t r[32];
-          tc_ld32(lane_addr + buf * 256 + cb * 32, r);
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
-            v[j] = (g == 8) ? x : fmaxf(x, 0.f);
-          }
-          if (g == 7) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s_logit = fmaf(v[j], s_bias[2304 + cb * 32 + j], s_logit);
-          }
-          if (g == 9) {
+          for (int ci = 0; ci < nch; ++ci) {
+            const int cb = 2 * ci + half;
+            uint32_t r[32];
+            tc_ld32(lane_addr + buf * 256 + cb * 32, r);
+            PROF_ADD(2);
+            float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              c_acc[0] = fmaf(v[j], s_bias[2560 + cb * 32 + j], c_acc[0]);
-              c_acc[1] = fmaf(v[j], s_bias[2560 + 128 + cb * 32 + j], c_acc[1]);
-              c_acc[2] = fmaf(v[j], s_bias[2560 + 256 + cb * 32 + j], c_acc[2]);
+              float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
+              v[j] = (g == 8) ? x : fmaxf(x, 0.f);
             }
-          }
-          if (stash && (!planes || g == 7 || g == 9)) {
-            float* dst = (g < 8) ? st.h[g] + m * 256 : (g == 8 ? st.feat + m * 256 : st.hr + m * 128);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
-              *reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-          }
-          if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi|lo, coalesced 512 B per warp
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb)
-              split_store8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
-          }
-          if (planes && g < 8) {   // ReLU bitmask of this 32-column chunk
-            uint32_t mw = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
-            st.mask[((size_t)g * st.Mpad + m) * 8 + cb] = mw;
-          }
-          if (g < 9) {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
               const int kblock = cb * 4 + kb;
               split_store8(v + kb * 8, A_hi + kblock * 2048 + row * 16, A_lo + kblock * 2048 + row * 16);
             }
-            if (cb & 1) {  // a 64-column block of the next layer's A operand is complete (128 arrivals: this half's 4 warps)
-              fence_async_smem();
-              mbar_arrive(BAR(B_AREADY + (cb >> 1)));
+            PROF_ADD(3);
+            fence_async_smem();
+            PROF_ADD(4);
+            mbar_arrive(BAR(B_AREADY + ci));     // 256 arrivals (both halves) complete block ci
+            PROF_ADD(5);
+          }
+        }
+        // pass 2 (overlaps the next layer's MMAs): re-read the accumulator for everything that is NOT needed by the
+        // next MMA: density / colour heads, fp32 side stash, bf16 operand planes, ReLU bitmasks
+        const bool need2 = (g == 7) || (g == 9) || stash;
+        if (need2) {
+#pragma unroll 1
+          for (int ci = 0; ci < nch; ++ci) {
+            const int cb = 2 * ci + half;
+            uint32_t r[32];
+            tc_ld32(lane_addr + buf * 256 + cb * 32, r);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
+              v[j] = (g == 8) ? x : fmaxf(x, 0.f);
+            }
+            if (g == 7) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s_logit = fmaf(v[j], s_bias[2304 + cb * 32 + j], s_logit);
+            }
+            if (g == 9) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                c_acc[0] = fmaf(v[j], s_bias[2560 + cb * 32 + j], c_acc[0]);
+                c_acc[1] = fmaf(v[j], s_bias[2560 + 128 + cb * 32 + j], c_acc[1]);
+                c_acc[2] = fmaf(v[j], s_bias[2560 + 256 + cb * 32 + j], c_acc[2]);
+              }
+            }
+            if (stash && (!planes || g == 7 || g == 9)) {
+              float* dst = (g < 8) ? st.h[g] + m * 256 : (g == 8 ? st.feat + m * 256 : st.hr + m * 128);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                __stcs(reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4), make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+            }
+            if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi|lo, coalesced 512 B per warp
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb)
+                split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
+            }
+            if (planes && g < 8) {   // ReLU bitmask of this 32-column chunk
+              uint32_t mw = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
+              __stcs(st.mask + ((size_t)g * st.Mpad + m) * 8 + cb, mw);
             }
           }
         }
         tc_fence_before();
         mbar_arrive(BAR(B_ACCEMPTY + buf));
+        PROF_ADD(6);
       }
       // ---- heads + per-sample record (half 1 hands its partial dot products to half 0) ----
       if (half == 1) {
@@ -383,6 +440,9 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         recs[m] = rec;
       }
     }
+#ifdef NNB_TC_PROFILE
+    if (warp == 2 && lane == 0 && blockIdx.x < 148) for (int i = 0; i < 7; ++i) g_tcprof2[blockIdx.x][i] = _pacc[i];
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -419,6 +479,14 @@ cudaError_t upload_stage_table() {
 
 }  // namespace
 
+#ifdef NNB_TC_PROFILE
+extern "C" int nnb_debug_tcprof(unsigned long long* host148x8) {
+  return (int)cudaMemcpyFromSymbol(host148x8, g_tcprof, sizeof(unsigned long long) * 148 * 8);
+}
+extern "C" int nnb_debug_tcprof2(unsigned long long* host148x8) {
+  return (int)cudaMemcpyFromSymbol(host148x8, g_tcprof2, sizeof(unsigned long long) * 148 * 8);
+}
+#endif
 size_t tc_bwd_workspace_extra();
 cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L, size_t img_t_offset, cudaStream_t st);
 

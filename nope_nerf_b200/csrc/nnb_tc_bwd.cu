@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), CL); }
-    for (int i = 0; i < 4; ++i) mbar_init(BAR(D_AREADY + i), 128);
+    for (int i = 0; i < 4; ++i) mbar_init(BAR(D_AREADY + i), 256);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(D_ACCFULL + i), 1); mbar_init(BAR(D_ACCEMPTY + i), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         const float* hr = P.hr + m * 128;
         float* dyr = P.dyr + m * 128;
 #pragma unroll 1
-        for (int jb = half * 8; jb < half * 8 + 8; ++jb) {
+        for (int ji = 0; ji < 8; ++ji) {
+          const int jb = 2 * ji + half;       // halves interleave 8-column groups: 64-column block b is done after ji = 4b+3
           float4 h0 = *reinterpret_cast<const float4*>(hr + jb * 8), h1 = *reinterpret_cast<const float4*>(hr + jb * 8 + 4);
           float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w}, v[8];
 #pragma unroll
@@ -231,11 +232,10 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           split_g(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16);
           *reinterpret_cast<float4*>(dyr + jb * 8) = make_float4(v[0] * inv_gscale, v[1] * inv_gscale, v[2] * inv_gscale, v[3] * inv_gscale);
           *reinterpret_cast<float4*>(dyr + jb * 8 + 4) = make_float4(v[4] * inv_gscale, v[5] * inv_gscale, v[6] * inv_gscale, v[7] * inv_gscale);
+          if ((ji & 3) == 3) { fence_async_smem(); mbar_arrive(BAR(D_AREADY + (ji >> 2))); }   // block 0 / 1 of g_yr complete (256 arrivals)
         }
       }
-      fence_async_smem();
-      mbar_arrive(BAR(D_AREADY + half));          // columns 64*half .. of g_yr (128 arrivals per block: this half's 4 warps)
-      mbar_arrive(BAR(D_AREADY + 2 + half));      // blocks 2,3 are empty in A version 0 (K = 128)
+      mbar_arrive(BAR(D_AREADY + 2)); mbar_arrive(BAR(D_AREADY + 3));     // blocks 2,3 are empty in A version 0 (K = 128)
       epi_bar();
       if (leader && write_dy) {   // dY planes of rgb_layers.0 (128 features = first 32 KB of each image)
         unsigned char* dst = P.dyp[9] + (size_t)tile * PLANE_TILE_128;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         const int nch = (pos == 5 || pos == 10) ? 1 : 4;   // 32-column chunks handled by this half
 #pragma unroll 1
         for (int ci = 0; ci < nch; ++ci) {
-          const int cb = half * nch + ci;
+          const int cb = (nch == 1) ? half : 2 * ci + half;    // halves share each 64-column block (ready after one chunk time)
           uint32_t r[32];
           tc_ld32(lane_addr + buf * 256 + cb * 32, r);
           float v[32];
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
               split_g(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16);
-            if (cb & 1) { fence_async_smem(); mbar_arrive(BAR(D_AREADY + (cb >> 1))); }
+            fence_async_smem(); mbar_arrive(BAR(D_AREADY + ci));
           }
         }
         tc_fence_before();

@@ -27,6 +27,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t}"
       ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware instead of spinning
 }
+// non-blocking probe: lets the caller overlap the ~110-cycle barrier round trip with other work
+__device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+// streaming (evict-first) 16-byte global store: stash / plane traffic must not push the weight images out of L2
+__device__ __forceinline__ void st_stream16(void* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -104,6 +113,20 @@ __device__ __forceinline__ void split_store8_bf16(const float* v, unsigned char*
   }
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void split_stream8_bf16(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<uint32_t*>(&hh);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+    hi[i] = hb;
+    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  st_stream16(hi_dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+  st_stream16(lo_dst, make_uint4(lo[0], lo[1], lo[2], lo[3]));
 }
 // instruction descriptor with explicit operand formats (0 = fp16, 1 = bf16) and major-ness (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t make_idesc_ex(int M, int N, int afmt, int bfmt, int amaj, int bmaj) {
