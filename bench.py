@@ -213,7 +213,9 @@ def run_ours(args):
                            "engine": args.engine, "frames_resident": N_FRAMES,
                            "l2_policy": "no flush: each step streams a 2.6 GB activation stash, far larger than the 126 MB L2"},
                 "e2e": {"value": round(e2e, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / K, 4),
-                        "h2d_bytes_per_step": int(3 * H * W * 4 + HD * WD * 4 + 64), "d2h_bytes_per_step": 4},
+                        "h2d_bytes_per_step": int(NRAYS * 3 * 32 + HD * WD * 4 + 64 + 16), "d2h_bytes_per_step": 4,
+                        "h2d_note": "host frames are page-locked: the loss kernel gathers the 1024x3 sampled pixels in place over PCIe "
+                                    "(one 32-B sector each) instead of copying the 24.9 MB frame; the 1 MB DPT map, camera_mat and idx are copied"},
                 "gpu_launches": 10 * K, "clocks": clocks, "roofline": roof,
                 "loss": float(ld["loss"].item()), "impl": "ours"}
         if world == 1 and not args.no_cpu_baseline:

@@ -211,11 +211,17 @@ class Trainer(object):
         fa.step()
 
     # ------------------------------------------------------------------------------------
-    def process_data_dict(self, data):
+    def process_data_dict(self, data, keep_pinned=False):
+        """training.py:164-175.  With keep_pinned, page-locked host frames are NOT copied: a render-only step touches
+        N pixels of the 3*H*W frame, which the loss kernel gathers in place over PCIe
+        (the reference ships the whole 25 MB frame to the device every step)."""
         device = self.device
-        img = data.get('img').to(device, non_blocking=True)
+        img = data.get('img'); dpt = data.get('img.dpt')
+        if not (keep_pinned and img.device.type == 'cpu' and img.is_pinned()):
+            img = img.to(device, non_blocking=True)
+        dpt = dpt.to(device, non_blocking=True)      # 1 MB; every kernel's ray setup reads it, so it lives in HBM
         img_idx = data.get('img.idx')
-        dpt = data.get('img.dpt').to(device, non_blocking=True).unsqueeze(1)
+        dpt = dpt.unsqueeze(1)
         camera_mat = data.get('img.camera_mat')
         _host_diag_check(camera_mat)
         camera_mat = camera_mat.to(device, non_blocking=True)
@@ -258,7 +264,7 @@ class Trainer(object):
             raise NotImplementedError("depth_consistency_weight != 0 has no producer in the reference either "
                                       "(training.py never passes d1_proj)")
         n_points = self.n_training_points
-        (img, depth_input, camera_mat_gt, scale_mat, img_idx) = self.process_data_dict(data)
+        (img, depth_input, camera_mat_gt, scale_mat, img_idx) = self.process_data_dict(data, keep_pinned=not use_ref_imgs)
         img_idx = int(img_idx)
         if use_ref_imgs:
             (ref_img, depth_ref, ref_idx) = self.process_data_reference(data)

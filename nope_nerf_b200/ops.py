@@ -35,9 +35,14 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _need_cuda(t, name):
-    if t is not None and not t.is_cuda:
-        raise RuntimeError("nope_nerf_b200: %s must live on a CUDA device (no CPU fallback exists)" % name)
+def _need_cuda(t, name, allow_pinned=False):
+    """device tensors only; `allow_pinned` additionally admits page-locked HOST tensors, which the kernels read in
+    place over PCIe through the unified address space (used for the frame / DPT map, of which a step touches N pixels)"""
+    if t is None or t.is_cuda:
+        return
+    if allow_pinned and t.is_pinned():
+        return
+    raise RuntimeError("nope_nerf_b200: %s must live on a CUDA device (no CPU fallback exists)" % name)
 
 
 def _f32c(t):
@@ -92,8 +97,9 @@ class RenderCall:
     def __init__(self, weights, c2w, cam, *, N, S, flags, engine, near, far, ray_idx=None, pixels=None, depth=None,
                  depth_map=None, scale=None, shift=None, noise=None, H=0, W=0, want_z_alpha=False, stash=False):
         for n_, t_ in (("weights", weights), ("c2w", c2w), ("camera_mat", cam), ("ray_idx", ray_idx), ("pixels", pixels),
-                       ("depth", depth), ("depth_map", depth_map), ("noise", noise)):
+                       ("depth", depth), ("noise", noise)):
             _need_cuda(t_, n_)
+        _need_cuda(depth_map, "depth_map")
         dev = weights.device
         self.keep = [weights, c2w, cam, ray_idx, pixels, depth, depth_map, scale, shift, noise]
         a = L.RenderArgs()
@@ -222,6 +228,7 @@ def loss_rgb_depth(rgb, depth_pred, depth_gt, mask, w_rgb, w_depth, rgb_l2, *, r
                    grad_scale=1.0):
     """returns (losses[4] = loss, loss_rgb, loss_depth, l2_mean ; g_rgb, g_depth_pred, g_depth_gt)"""
     N = rgb.shape[0]; dev = rgb.device
+    _need_cuda(img, "img", allow_pinned=True); _need_cuda(rgb_gt, "rgb_gt")
     out = torch.empty(4, device=dev)
     g_rgb = torch.empty(N, 3, device=dev); g_dp = torch.empty(N, device=dev); g_dg = torch.empty(N, device=dev)
     HW = 0 if img is None else (img.shape[-1] if img.dim() == 2 else img.shape[-1] * img.shape[-2])
