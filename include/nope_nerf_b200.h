@@ -102,6 +102,24 @@ int nnb_pose_fwd(const float* r, const float* t, const float* init_c2w /*[V,16] 
 int nnb_pose_bwd(const float* r, const float* t, const float* init_c2w, int32_t cam_id, const float* g_c2w,
                  float* g_r, float* g_t, void* stream);
 
+/* CUDA-graph friendly variants: per-step host scalars (camera index, Adam step, learning rate, frame pointer) are read
+ * from DEVICE memory so one captured graph of the whole training step can be replayed for every frame. */
+int nnb_pose_fwd_dev(const float* r, const float* t, const float* init_c2w, const int32_t* cam_id_dev, float* c2w, void* stream);
+int nnb_pose_bwd_dev(const float* r, const float* t, const float* init_c2w, const int32_t* cam_id_dev, const float* g_c2w, float* g_r,
+                     float* g_t, void* stream);
+/* Learn_Distortion.forward (model/distortions.py:19-27): out2 = {scale_eff, shift} of view *cam_id_dev; and its adjoint */
+int nnb_distortion_fwd_dev(const float* scales, const float* shifts, int32_t V, const int32_t* cam_id_dev, int32_t fix_scaleN, float* out2,
+                           void* stream);
+int nnb_distortion_bwd_dev(const float* scales, int32_t V, const int32_t* cam_id_dev, int32_t fix_scaleN, const float* g_scale_shift,
+                           float* g_scales, float* g_shifts, void* stream);
+int nnb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int32_t* step_dev, const float* lr_dev, float beta1,
+                      float beta2, float eps, void* stream);
+int nnb_counter_incr(int32_t* counters, int32_t n, void* stream);
+int nnb_loss_rgb_depth_indirect(const float* rgb, const float* const* img_pp /* device pointer to the frame pointer */, const int64_t* ray_idx,
+                                int32_t HW, const float* depth_pred, const float* depth_gt, const uint8_t* mask, int32_t N, float w_rgb,
+                                float w_depth, int32_t rgb_l2, float grad_scale, float* out_losses, float* g_rgb, float* g_depth_pred,
+                                float* g_depth_gt, void* stream);
+
 /* Loss.forward photometric + depth-L1 terms (model/losses.py:27-32,59-61,192,196-202) fused with
  * the cotangent seeds of nnb_render_bwd.  rgb_gt is either explicit [N,3] or gathered from a planar
  * image [3,H*W] at ray_idx (training.py:258-259).  out_losses = {loss, loss_rgb, loss_depth, l2_mean}. */

@@ -49,6 +49,14 @@ def _load():
     lib.nnb_chamfer.argtypes = [_f, C.c_int32, _f, C.c_int32, _f, _f, _f, C.c_float, _f, _f, C.c_void_p]
     lib.nnb_adam_step.argtypes = [_f, _f, _f, _f, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.nnb_profile_events.argtypes = [C.c_void_p, C.c_int32]
+    lib.nnb_pose_fwd_dev.argtypes = [_f, _f, _f, _f, _f, C.c_void_p]
+    lib.nnb_pose_bwd_dev.argtypes = [_f, _f, _f, _f, _f, _f, _f, C.c_void_p]
+    lib.nnb_distortion_fwd_dev.argtypes = [_f, _f, C.c_int32, _f, C.c_int32, _f, C.c_void_p]
+    lib.nnb_distortion_bwd_dev.argtypes = [_f, C.c_int32, _f, C.c_int32, _f, _f, _f, C.c_void_p]
+    lib.nnb_adam_step_dev.argtypes = [_f, _f, _f, _f, C.c_int64, _f, _f, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.nnb_counter_incr.argtypes = [_f, C.c_int32, C.c_void_p]
+    lib.nnb_loss_rgb_depth_indirect.argtypes = [_f, _f, _f, C.c_int32, _f, _f, _f, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, _f, _f,
+                                                _f, _f, C.c_void_p]
     for name in ("nnb_refstage_fwd", "nnb_refstage_bwd"):
         if hasattr(lib, name):
             getattr(lib, name).restype = C.c_int

@@ -13,9 +13,13 @@ cudaError_t tc_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaS
 size_t tc_workspace_extra(int N, int S, uint32_t flags);
 bool tc_supports(int S);
 #endif
-cudaError_t launch_pose_fwd(const float*, const float*, const float*, int, float*, cudaStream_t);
-cudaError_t launch_pose_bwd(const float*, const float*, const float*, int, const float*, float*, float*, cudaStream_t);
-cudaError_t launch_loss(const float*, const float*, const float*, const int64_t*, int, const float*, const float*, const uint8_t*,
+cudaError_t launch_pose_fwd(const float*, const float*, const float*, int, const int*, float*, cudaStream_t);
+cudaError_t launch_pose_bwd(const float*, const float*, const float*, int, const int*, const float*, float*, float*, cudaStream_t);
+cudaError_t launch_distortion_fwd(const float*, const float*, int, const int*, int, float*, cudaStream_t);
+cudaError_t launch_distortion_bwd(const float*, int, const int*, int, const float*, float*, float*, cudaStream_t);
+cudaError_t launch_adam_dev(float*, const float*, float*, float*, int64_t, const int*, const float*, float, float, float, cudaStream_t);
+cudaError_t launch_incr(int*, int, cudaStream_t);
+cudaError_t launch_loss(const float*, const float*, const float*, const float* const*, const int64_t*, int, const float*, const float*, const uint8_t*,
                         int, float, float, int, float, float*, float*, float*, float*, cudaStream_t);
 cudaError_t launch_chamfer(const float*, int, const float*, int, int*, int*, float*, float, float*, float*, cudaStream_t);
 cudaError_t launch_adam(float*, const float*, float*, float*, int64_t, int, float, float, float, float, cudaStream_t);
@@ -116,12 +120,44 @@ int nnb_render_bwd(const nnb_render_bwd_args* b, void* stream) {
 
 int nnb_pose_fwd(const float* r, const float* t, const float* init, int32_t cam, float* c2w, void* stream) {
   if (!r || !t || !c2w || cam < 0) return fail(-3, "nnb_pose_fwd: bad arguments");
-  cudaError_t e = launch_pose_fwd(r, t, init, cam, c2w, (cudaStream_t)stream);
+  cudaError_t e = launch_pose_fwd(r, t, init, cam, nullptr, c2w, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_pose_fwd");
+}
+int nnb_pose_fwd_dev(const float* r, const float* t, const float* init, const int32_t* cam_dev, float* c2w, void* stream) {
+  if (!r || !t || !c2w || !cam_dev) return fail(-3, "nnb_pose_fwd_dev: bad arguments");
+  cudaError_t e = launch_pose_fwd(r, t, init, 0, cam_dev, c2w, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_pose_fwd_dev");
+}
+int nnb_pose_bwd_dev(const float* r, const float* t, const float* init, const int32_t* cam_dev, const float* g, float* gr, float* gt, void* stream) {
+  if (!r || !t || !g || !cam_dev) return fail(-3, "nnb_pose_bwd_dev: bad arguments");
+  cudaError_t e = launch_pose_bwd(r, t, init, 0, cam_dev, g, gr, gt, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_pose_bwd_dev");
+}
+int nnb_distortion_fwd_dev(const float* scales, const float* shifts, int32_t V, const int32_t* cam_dev, int32_t fix_last, float* out2, void* stream) {
+  if (!scales || !shifts || !cam_dev || !out2 || V <= 0) return fail(-3, "nnb_distortion_fwd_dev: bad arguments");
+  cudaError_t e = launch_distortion_fwd(scales, shifts, V, cam_dev, fix_last, out2, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_distortion_fwd_dev");
+}
+int nnb_distortion_bwd_dev(const float* scales, int32_t V, const int32_t* cam_dev, int32_t fix_last, const float* g_ss, float* g_scales,
+                           float* g_shifts, void* stream) {
+  if (!scales || !cam_dev || !g_ss || V <= 0) return fail(-3, "nnb_distortion_bwd_dev: bad arguments");
+  cudaError_t e = launch_distortion_bwd(scales, V, cam_dev, fix_last, g_ss, g_scales, g_shifts, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_distortion_bwd_dev");
+}
+int nnb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int32_t* step_dev, const float* lr_dev, float b1, float b2,
+                      float eps, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || !step_dev || !lr_dev) return fail(-3, "nnb_adam_step_dev: bad arguments");
+  cudaError_t e = launch_adam_dev(p, g, m, v, n, step_dev, lr_dev, b1, b2, eps, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_adam_step_dev");
+}
+int nnb_counter_incr(int32_t* counters, int32_t n, void* stream) {
+  if (!counters || n <= 0 || n > 32) return fail(-3, "nnb_counter_incr: bad arguments");
+  cudaError_t e = launch_incr(counters, n, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_counter_incr");
 }
 int nnb_pose_bwd(const float* r, const float* t, const float* init, int32_t cam, const float* g, float* gr, float* gt, void* stream) {
   if (!r || !t || !g || cam < 0) return fail(-3, "nnb_pose_bwd: bad arguments");
-  cudaError_t e = launch_pose_bwd(r, t, init, cam, g, gr, gt, (cudaStream_t)stream);
+  cudaError_t e = launch_pose_bwd(r, t, init, cam, nullptr, g, gr, gt, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_pose_bwd");
 }
 
@@ -130,9 +166,18 @@ int nnb_loss_rgb_depth(const float* rgb, const float* rgb_gt, const float* img, 
                        int32_t rgb_l2, float grad_scale, float* out, float* g_rgb, float* g_dp, float* g_dg, void* stream) {
   if (!rgb || !(rgb_gt || (img && ray_idx)) || !dp || !dg || !mask || !out || !g_rgb || !g_dp || !g_dg || N <= 0)
     return fail(-3, "nnb_loss_rgb_depth: bad arguments");
-  cudaError_t e = launch_loss(rgb, rgb_gt, img, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, rgb_l2, grad_scale, out, g_rgb, g_dp, g_dg,
+  cudaError_t e = launch_loss(rgb, rgb_gt, img, nullptr, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, rgb_l2, grad_scale, out, g_rgb, g_dp, g_dg,
                               (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_loss_rgb_depth");
+}
+int nnb_loss_rgb_depth_indirect(const float* rgb, const float* const* img_pp, const int64_t* ray_idx, int32_t HW, const float* dp, const float* dg,
+                                const uint8_t* mask, int32_t N, float w_rgb, float w_depth, int32_t rgb_l2, float grad_scale, float* out,
+                                float* g_rgb, float* g_dp, float* g_dg, void* stream) {
+  if (!rgb || !img_pp || !ray_idx || !dp || !dg || !mask || !out || !g_rgb || !g_dp || !g_dg || N <= 0)
+    return fail(-3, "nnb_loss_rgb_depth_indirect: bad arguments");
+  cudaError_t e = launch_loss(rgb, nullptr, nullptr, img_pp, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, rgb_l2, grad_scale, out, g_rgb, g_dp,
+                              g_dg, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_loss_rgb_depth_indirect");
 }
 
 int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, int32_t* ixy, int32_t* iyx, float* loss, float weight,

@@ -19,8 +19,9 @@ __device__ void exp_so3(const float r[3], float R[9], float* n_out, float* A_out
   *n_out = n0; *A_out = A; *B_out = B;
 }
 
-__global__ void pose_fwd_k(const float* r, const float* t, const float* init, int cam, float* c2w) {
+__global__ void pose_fwd_k(const float* r, const float* t, const float* init, int cam, const int* cam_dev, float* c2w) {
   if (threadIdx.x != 0) return;
+  if (cam_dev) cam = *cam_dev;
   float rv[3] = {r[3 * cam], r[3 * cam + 1], r[3 * cam + 2]}, R[9], n0, A, B;
   exp_so3(rv, R, &n0, &A, &B);
   float c[16] = {R[0], R[1], R[2], t[3 * cam], R[3], R[4], R[5], t[3 * cam + 1], R[6], R[7], R[8], t[3 * cam + 2], 0, 0, 0, 1};
@@ -33,8 +34,9 @@ __global__ void pose_fwd_k(const float* r, const float* t, const float* init, in
   } else for (int i = 0; i < 16; ++i) c2w[i] = c[i];
 }
 
-__global__ void pose_bwd_k(const float* r, const float* t, const float* init, int cam, const float* g_c2w, float* g_r, float* g_t) {
+__global__ void pose_bwd_k(const float* r, const float* t, const float* init, int cam, const int* cam_dev, const float* g_c2w, float* g_r, float* g_t) {
   if (threadIdx.x != 0) return;
+  if (cam_dev) cam = *cam_dev;
   float g[16];
   if (init) {  // c2w = C @ I  ->  gC = g @ I^T
     const float* I = init + 16 * cam;
@@ -85,10 +87,11 @@ __device__ float block_sum(float v, float* sh) {
   return sh[32];
 }
 
-__global__ void loss_rgb_depth_k(const float* rgb, const float* rgb_gt, const float* img, const int64_t* ray_idx, int HW,
+__global__ void loss_rgb_depth_k(const float* rgb, const float* rgb_gt, const float* img, const float* const* img_pp, const int64_t* ray_idx, int HW,
                                  const float* dp, const float* dg, const uint8_t* mask, int N, float w_rgb, float w_depth,
                                  int rgb_l2, float grad_scale, float* out, float* g_rgb, float* g_dp, float* g_dg) {
   __shared__ float sh[33];
+  if (img_pp) img = *img_pp;      // frame pointer fetched from device memory (lets a captured CUDA graph follow a new frame)
   float l1 = 0.f, l2 = 0.f, ld = 0.f, cnt = 0.f;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     for (int c = 0; c < 3; ++c) {
@@ -156,6 +159,39 @@ __global__ void chamfer_acc_k(const float* A, int P, const float* B, const int* 
   if (threadIdx.x == 0) atomicAdd(loss, tot / (float)P);
 }
 
+// Learn_Distortion.forward (model/distortions.py:19-27) for a device-resident camera index:
+//   scale_eff = fixed-last-view ? 1 : max(scale, 0.01) ; shift = shifts[cam]   -> out[2]
+__global__ void distortion_fwd_k(const float* scales, const float* shifts, int V, const int* cam_dev, int fix_last, float* out) {
+  if (threadIdx.x != 0) return;
+  int cam = *cam_dev;
+  float s = scales[cam];
+  if (s < 0.01f) s = 0.01f;
+  if (fix_last && cam == V - 1) s = 1.f;
+  out[0] = s; out[1] = shifts[cam];
+}
+// its adjoint: the constant replacements carry no gradient
+__global__ void distortion_bwd_k(const float* scales, int V, const int* cam_dev, int fix_last, const float* g_ss, float* g_scales, float* g_shifts) {
+  if (threadIdx.x != 0) return;
+  int cam = *cam_dev;
+  bool live = scales[cam] >= 0.01f && !(fix_last && cam == V - 1);
+  if (g_scales && live) g_scales[cam] += g_ss[0];
+  if (g_shifts) g_shifts[cam] += g_ss[1];
+}
+// Adam with device-resident step counter and learning rate (CUDA-graph friendly): state = {step (int32), lr (float)}
+__global__ void adam_dev_k(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, const float* lr_dev, float b1, float b2, float eps) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int step = *step_dev;
+  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  const float lr_bc1 = *lr_dev / bc1, rsqrt_bc2 = rsqrtf(bc2);
+  float gi = g[i];
+  float mi = b1 * m[i] + (1.f - b1) * gi;
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] -= lr_bc1 * mi / (sqrtf(vi) * rsqrt_bc2 + eps);
+}
+__global__ void incr_k(int* a, int n) { if (threadIdx.x < n) a[threadIdx.x] += 1; }
+
 __global__ void adam_k(float* p, const float* g, float* m, float* v, int64_t n, float lr_bc1, float rsqrt_bc2, float b1, float b2, float eps) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -168,16 +204,28 @@ __global__ void adam_k(float* p, const float* g, float* m, float* v, int64_t n, 
 
 }  // namespace
 
-cudaError_t launch_pose_fwd(const float* r, const float* t, const float* init, int cam, float* c2w, cudaStream_t st) {
-  pose_fwd_k<<<1, 32, 0, st>>>(r, t, init, cam, c2w); return cudaGetLastError();
+cudaError_t launch_pose_fwd(const float* r, const float* t, const float* init, int cam, const int* cam_dev, float* c2w, cudaStream_t st) {
+  pose_fwd_k<<<1, 32, 0, st>>>(r, t, init, cam, cam_dev, c2w); return cudaGetLastError();
 }
-cudaError_t launch_pose_bwd(const float* r, const float* t, const float* init, int cam, const float* g, float* gr, float* gt, cudaStream_t st) {
-  pose_bwd_k<<<1, 32, 0, st>>>(r, t, init, cam, g, gr, gt); return cudaGetLastError();
+cudaError_t launch_pose_bwd(const float* r, const float* t, const float* init, int cam, const int* cam_dev, const float* g, float* gr, float* gt,
+                            cudaStream_t st) {
+  pose_bwd_k<<<1, 32, 0, st>>>(r, t, init, cam, cam_dev, g, gr, gt); return cudaGetLastError();
 }
-cudaError_t launch_loss(const float* rgb, const float* rgb_gt, const float* img, const int64_t* ray_idx, int HW, const float* dp,
-                        const float* dg, const uint8_t* mask, int N, float w_rgb, float w_depth, int l2, float gscale, float* out,
+cudaError_t launch_distortion_fwd(const float* sc, const float* sh, int V, const int* cam_dev, int fix_last, float* out, cudaStream_t st) {
+  distortion_fwd_k<<<1, 32, 0, st>>>(sc, sh, V, cam_dev, fix_last, out); return cudaGetLastError();
+}
+cudaError_t launch_distortion_bwd(const float* sc, int V, const int* cam_dev, int fix_last, const float* g_ss, float* g_sc, float* g_sh, cudaStream_t st) {
+  distortion_bwd_k<<<1, 32, 0, st>>>(sc, V, cam_dev, fix_last, g_ss, g_sc, g_sh); return cudaGetLastError();
+}
+cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, const float* lr_dev, float b1, float b2,
+                            float eps, cudaStream_t st) {
+  adam_dev_k<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, step_dev, lr_dev, b1, b2, eps); return cudaGetLastError();
+}
+cudaError_t launch_incr(int* a, int n, cudaStream_t st) { incr_k<<<1, 32, 0, st>>>(a, n); return cudaGetLastError(); }
+cudaError_t launch_loss(const float* rgb, const float* rgb_gt, const float* img, const float* const* img_pp, const int64_t* ray_idx, int HW,
+                        const float* dp, const float* dg, const uint8_t* mask, int N, float w_rgb, float w_depth, int l2, float gscale, float* out,
                         float* g_rgb, float* g_dp, float* g_dg, cudaStream_t st) {
-  loss_rgb_depth_k<<<1, 1024, 0, st>>>(rgb, rgb_gt, img, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, l2, gscale, out, g_rgb, g_dp, g_dg);
+  loss_rgb_depth_k<<<1, 1024, 0, st>>>(rgb, rgb_gt, img, img_pp, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, l2, gscale, out, g_rgb, g_dp, g_dg);
   return cudaGetLastError();
 }
 cudaError_t launch_chamfer(const float* X, int P, const float* Y, int Q, int* ixy, int* iyx, float* loss, float weight, float* gX,

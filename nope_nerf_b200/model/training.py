@@ -38,6 +38,39 @@ class _FlatAdam:
         self.flat_slices = flat_slices
         self.m = self.v = None
         self.ok = self._supported()
+        self.nsteps = 0              # steps taken so far (source of truth shared with the CUDA-graph path)
+        self._synced = True
+        try:
+            optimizer.register_state_dict_pre_hook(lambda opt: self.sync_step_tensors())
+        except Exception:
+            pass
+
+    def sync_step_tensors(self):
+        """optimizer.state[p]['step'] tensors follow `nsteps` lazily (the graph path does not touch them per step)"""
+        for st in self.opt.state.values():
+            if 'step' in st: st['step'].fill_(float(self.nsteps))
+        self._synced = True
+
+    def ensure_state(self):
+        """allocate / adopt the moment buffers without stepping"""
+        g = self.opt.param_groups[0]
+        if self.flat_param is not None:
+            flat = self.flat_param(); plist = list(g['params']); n = flat.numel()
+            if self.m is None or self.m.device != flat.device:
+                self.m = torch.zeros(n, device=flat.device); self.v = torch.zeros(n, device=flat.device)
+            for p, (o, k, sh) in zip(plist, self.flat_slices):
+                self._state(p, self.m[o:o + k].view(sh), self.v[o:o + k].view(sh))
+        else:
+            if self.m is None:
+                self.m = {}; self.v = {}
+            for p in g['params']:
+                key = id(p)
+                if key not in self.m or self.m[key].shape != p.shape or self.m[key].device != p.device:
+                    self.m[key] = torch.zeros_like(p); self.v[key] = torch.zeros_like(p)
+                self._state(p, self.m[key], self.v[key])
+        st0 = next(iter(self.opt.state.values()), None)
+        if st0 is not None and self._synced and int(st0['step']) > self.nsteps:
+            self.nsteps = int(st0['step'])          # e.g. optimizer state loaded from a checkpoint
 
     def _supported(self):
         o = self.opt
@@ -77,13 +110,14 @@ class _FlatAdam:
             if self.m is None or self.m.device != flat.device:
                 self.m = torch.zeros(n, device=flat.device); self.v = torch.zeros(n, device=flat.device)
             sts = [self._state(p, self.m[o:o + k].view(sh), self.v[o:o + k].view(sh)) for p, (o, k, sh) in zip(plist, self.flat_slices)]
-            step = int(sts[0]['step']) + 1
+            if not self._synced or int(sts[0]['step']) != self.nsteps: self.sync_step_tensors()
+            step = self.nsteps + 1
             gflat_ptr_ok = all(p.grad is not None and p.grad.data_ptr() == g0.data_ptr() + 4 * o for p, (o, k, sh) in zip(plist, self.flat_slices))
             if not gflat_ptr_ok:
                 return self.opt.step()
             gflat = torch.as_strided(g0, (n,), (1,))      # the installed .grad views alias one flat gradient buffer
             ops.adam_step(flat, gflat, self.m, self.v, step, lr, b1, b2, eps)
-            for st in sts: st['step'] += 1
+            self.nsteps = step; self._synced = False
         else:
             if self.m is None:
                 self.m = {}; self.v = {}
@@ -92,10 +126,10 @@ class _FlatAdam:
                 if key not in self.m or self.m[key].shape != p.shape or self.m[key].device != p.device:
                     self.m[key] = torch.zeros_like(p); self.v[key] = torch.zeros_like(p)
                 st = self._state(p, self.m[key], self.v[key])
-                step = int(st['step']) + 1
+                step = self.nsteps + 1
                 gr = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 ops.adam_step(p.data, gr, self.m[key], self.v[key], step, lr, b1, b2, eps)
-                st['step'] += 1
+            self.nsteps += 1; self._synced = False
 
 
 def _host_diag_check(camera_mat):
@@ -106,6 +140,146 @@ def _host_diag_check(camera_mat):
     off = m - torch.diag(torch.diagonal(m))
     if off.abs().max() != 0 or m[2, 2] != -1 or m[3, 3] != 1:
         raise NotImplementedError("camera_mat must be diag(kx, ky, -1, 1)")
+
+
+class _GraphStep:
+    """The whole render-only training step (pose exp-map, distortion, pixel sampling, render forward, losses, backward,
+    [all-reduce], Adam x3) captured ONCE as a CUDA graph and replayed per frame.  Everything that changes from step to
+    step is read from device memory: camera index, frame pointer, DPT map, camera matrix, Adam step counters, learning
+    rates.  The first call runs the same body eagerly (that IS that call's training step and warms every lazy
+    initialisation), the second call captures, later calls replay."""
+
+    def __init__(self, tr, h, w, hd, wd, w_rgb, w_depth, rgb_l2):
+        self.tr = tr; self.key = (h, w, hd, wd, float(w_rgb), float(w_depth), bool(rgb_l2))
+        dev = tr.device
+        self.h, self.w, self.hd, self.wd = h, w, hd, wd
+        self.w_rgb, self.w_depth, self.rgb_l2 = w_rgb, w_depth, rgb_l2
+        self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.imgp = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.dpt = torch.zeros(hd, wd, device=dev)
+        self.cam = torch.zeros(4, 4, device=dev); self.cam_host = None
+        self.ss = torch.zeros(2, device=dev)               # effective (scale, shift) of the current view
+        self.c2w = torch.zeros(4, 4, device=dev)
+        self.small = torch.zeros(16 + 2, device=dev)       # [g_c2w | g_scale_shift]
+        self.steps = torch.zeros(3, dtype=torch.int32, device=dev)   # Adam step counters: mlp, pose, distortion
+        self.lrs = torch.zeros(3, device=dev); self.lr_host = [None, None, None]
+        self.out4 = torch.zeros(4, device=dev)
+        N = tr.n_training_points // tr.world if tr.dp_mode == 'rays' else tr.n_training_points
+        self.g_rgb = torch.zeros(N, 3, device=dev); self.g_dp = torch.zeros(N, device=dev); self.g_dg = torch.zeros(N, device=dev)
+        self.graph = None; self.calls = 0; self.keep = []; self.img_ref = None
+        self.fadams = None
+
+    def _adams(self):
+        tr = self.tr
+        if self.fadams is None:
+            from .official_nerf import PARAM_SLICES
+            net = tr.model.renderer.model
+            fa = [tr._fadam_for(tr.optimizer, True), tr._fadam_for(tr.optimizer_pose, False), tr._fadam_for(tr.optimizer_distortion, False)]
+            self.fadams = fa
+        return self.fadams
+
+    def eligible_optimizers(self):
+        return all(fa.ok for fa in self._adams())
+
+    def body(self):
+        tr = self.tr; dev = tr.device
+        pose, dnet = tr.pose_param_net, tr.distortion_net
+        net = tr.model.renderer.model; rend = tr.model.renderer
+        h, w = self.h, self.w
+        gbuf, gv = tr._grad_buffer()
+        self.small.zero_()
+        g_c2w = self.small[:16].view(4, 4); g_ss = self.small[16:18]
+        ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx, dnet.fix_scaleN, self.ss)
+        n_points = tr.n_training_points
+        ray_idx = torch.randperm(h * w, device=dev)[:n_points]                    # training.py:257
+        S = int(rend.cfg['num_points'])
+        noise = None
+        if rend.cfg['sample_option'] == 'uniform':
+            noise = torch.rand(1, n_points, S, device=dev)[0]                      # rendering.py:189
+        if tr.world > 1 and tr.dp_mode == 'rays':
+            ray_idx = ray_idx[tr.rank::tr.world].contiguous()
+            if noise is not None: noise = noise[tr.rank::tr.world].contiguous()
+        n_local = ray_idx.shape[0]
+        init = None if pose.init_c2w is None else pose.init_c2w.detach()
+        ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx, self.c2w)
+        flags = ops.flags_from_cfg(rend.cfg, net.occ_activation, eval_=False, shift_first=tr.shift_first)
+        ndc = rend.cfg['sample_option'] == 'ndc'
+        call = ops.RenderCall(net.flat_weights(), self.c2w, self.cam, N=n_local, S=S, flags=flags,
+                              engine=rend.engine if rend.engine is not None else ops.default_engine(),
+                              near=0.0 if ndc else rend.depth_range[0], far=1.0 if ndc else rend.depth_range[1],
+                              ray_idx=ray_idx, depth_map=self.dpt, scale=self.ss[0:1], shift=self.ss[1:2], noise=noise, H=h, W=w, stash=True)
+        gs = 1.0 / tr.world
+        ops.loss_rgb_depth_indirect(call.rgb, call.depth_pred, call.depth_gt, call.mask, self.w_rgb, self.w_depth, self.rgb_l2, self.imgp,
+                                    ray_idx, h * w, self.out4, self.g_rgb, self.g_dp, self.g_dg, grad_scale=gs)
+        ws = call.ws
+        call.pooled = False                                 # memory referenced by a captured graph never returns to the pool
+        call.backward(self.g_rgb, self.g_dp, None if tr.detach_gt_depth else self.g_dg, gbuf[:L.NUM_PARAMS], g_c2w, None, None, g_ss)
+        self.keep.append((call, ws, ray_idx, noise))        # graph-owned memory stays referenced (and out of the workspace pool)
+        ops.pose_bwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx, g_c2w,
+                         gv['r'] if pose.r.requires_grad else None, gv['t'] if pose.t.requires_grad else None)
+        ops.distortion_bwd_dev(dnet.global_scales.detach(), self.idx, dnet.fix_scaleN, g_ss,
+                               gv['scales'] if dnet.global_scales.requires_grad else None,
+                               gv['shifts'] if dnet.global_shifts.requires_grad else None)
+        gv['losses'].copy_(self.out4 * gs if tr.world > 1 else self.out4)
+        if tr.world > 1:
+            torch.distributed.all_reduce(gbuf, group=tr.dp_group)
+        # optimizers: device-side step counters / learning rates
+        ops.counter_incr(self.steps)
+        fa_m, fa_p, fa_d = self._adams()
+        gm = tr.optimizer.param_groups[0]; b1, b2 = gm['betas']
+        flat = net.flat_weights()
+        ops.adam_step_dev(flat, gbuf[:L.NUM_PARAMS], fa_m.m, fa_m.v, self.steps[0:1], self.lrs[0:1], b1, b2, gm['eps'])
+        for fa, opt, k in ((fa_p, tr.optimizer_pose, 1), (fa_d, tr.optimizer_distortion, 2)):
+            g = opt.param_groups[0]; b1, b2 = g['betas']
+            for p in g['params']:
+                if p.requires_grad and p.grad is not None:
+                    ops.adam_step_dev(p.data, p.grad, fa.m[id(p)], fa.v[id(p)], self.steps[k:k + 1], self.lrs[k:k + 1], b1, b2, g['eps'])
+
+    def run(self, data):
+        tr = self.tr; dev = tr.device
+        img = data.get('img')
+        if img.device.type == 'cpu' and not img.is_pinned():
+            img = img.to(dev, non_blocking=True)
+        self.img_ref = img
+        self.imgp.fill_(img.data_ptr())
+        self.idx.fill_(int(data.get('img.idx')))
+        self.dpt.copy_(data.get('img.dpt').reshape(self.hd, self.wd), non_blocking=True)
+        cm = data.get('img.camera_mat')
+        if self.cam_host is None or (cm.device.type == 'cpu' and not torch.equal(cm.reshape(4, 4), self.cam_host)):
+            _host_diag_check(cm)
+            self.cam_host = cm.reshape(4, 4).clone() if cm.device.type == 'cpu' else None
+            self.cam.copy_(cm.reshape(4, 4))
+        elif cm.device.type != 'cpu':
+            self.cam.copy_(cm.reshape(4, 4))
+        fas = self._adams()
+        opts = (tr.optimizer, tr.optimizer_pose, tr.optimizer_distortion)
+        for k, (fa, opt) in enumerate(zip(fas, opts)):
+            fa.ensure_state()
+            lr = float(opt.param_groups[0]['lr'])
+            if self.lr_host[k] != lr:
+                self.lrs[k:k + 1].fill_(lr); self.lr_host[k] = lr
+        want = [fa.nsteps for fa in fas]
+        if getattr(self, 'steps_host', None) != want:
+            self.steps.copy_(torch.tensor(want, dtype=torch.int32)); self.steps_host = list(want)
+        self.calls += 1
+        if self.calls == 1 or not tr.use_cuda_graph:
+            self.body()                                   # eager (also the warm-up of every lazy initialisation)
+            self.keep.clear()
+        else:
+            if self.graph is None:
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.body()
+            self.graph.replay()
+        for fa in fas:
+            fa.nsteps += 1; fa._synced = False
+        self.steps_host = [fa.nsteps for fa in fas]
+        gv_losses = tr._gbuf[-4:]
+        zero = torch.zeros((), device=dev)
+        return {'loss': gv_losses[0], 'loss_rgb': gv_losses[1], 'loss_depth': gv_losses[2], 'l2_mean': gv_losses[3],
+                'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': zero, 'loss_rgb_s': zero, 'loss_depth_consistency': zero,
+                'scale': self.ss[0:1], 'shift': self.ss[1:2]}
 
 
 class Trainer(object):
@@ -155,6 +329,9 @@ class Trainer(object):
         # fused flat-buffer Adam; optimizers remain the caller's objects
         self.fused_adam = kwargs.get('fused_adam', True)
         self._fadam = {}
+        # whole-step CUDA graph for render-only steps (statistically, not stream-, identical pixel/jitter draws)
+        self.use_cuda_graph = kwargs.get('use_cuda_graph', os.environ.get('NNB_CUDA_GRAPH', '1') == '1')
+        self._gsteps = {}
 
     # ------------------------------------------------------------------------------------
     def _grad_buffer(self):
@@ -188,6 +365,9 @@ class Trainer(object):
         if self.focal_net:
             self.focal_net.train(); self.optimizer_focal.zero_grad()
         if self.distortion_net: self.distortion_net.train()
+        gs = self._graph_step_or_none(data, epoch, scheduling_start)
+        if gs is not None:
+            return gs.run(data)          # fixed kernel sequence; replayed as one CUDA graph when use_cuda_graph
         loss_dict = self.compute_loss(data, it=it, epoch=epoch, scheduling_start=scheduling_start,
                                       out_render_path=render_path, backward=True)
         self._opt_step(self.optimizer, mlp=True)
@@ -196,9 +376,7 @@ class Trainer(object):
         if self.optimizer_distortion: self._opt_step(self.optimizer_distortion)
         return loss_dict
 
-    def _opt_step(self, opt, mlp=False):
-        if not self.fused_adam:
-            return opt.step()
+    def _fadam_for(self, opt, mlp):
         fa = self._fadam.get(id(opt))
         if fa is None:
             if mlp:
@@ -208,7 +386,39 @@ class Trainer(object):
             else:
                 fa = _FlatAdam(opt)
             self._fadam[id(opt)] = fa
-        fa.step()
+        return fa
+
+    def _opt_step(self, opt, mlp=False):
+        if not self.fused_adam:
+            return opt.step()
+        self._fadam_for(opt, mlp).step()
+
+    def _graph_step_or_none(self, data, epoch, scheduling_start):
+        """fast path: the whole step as one fixed kernel sequence / CUDA graph (render + rgb + depth losses only)"""
+        if not self.fused_adam or self.optimizer_focal or self.pose_param_net is None or self.distortion_net is None:
+            return None
+        if self.optimizer_pose is None or self.optimizer_distortion is None:
+            return None
+        names = ['rgb_weight', 'depth_weight', 'pc_weight', 'rgb_s_weight', 'depth_consistency_weight', 'weight_dist_2nd_loss',
+                 'weight_dist_1st_loss']
+        wts = {n: self.anneal(getattr(self, n)[0], getattr(self, n)[1], scheduling_start, self.annealing_epochs, epoch) for n in names}
+        if any(wts[n] != 0.0 for n in names[2:]) or (wts['rgb_weight'] == 0.0 and wts['depth_weight'] == 0.0):
+            return None
+        rgb_l2 = not (epoch < self.annealing_epochs + scheduling_start)
+        img = data.get('img'); dpt = data.get('img.dpt')
+        _, _, h, w = img.shape
+        hd, wd = dpt.shape[-2:]
+        key = (h, w, hd, wd, float(wts['rgb_weight']), float(wts['depth_weight']), bool(rgb_l2))
+        gs = self._gsteps.get(key)
+        if gs is None:
+            gs = _GraphStep(self, h, w, hd, wd, wts['rgb_weight'], wts['depth_weight'], rgb_l2)
+            if not gs.eligible_optimizers():
+                self._gsteps[key] = False
+                return None
+            self._gsteps[key] = gs
+        if gs is False:
+            return None
+        return gs
 
     # ------------------------------------------------------------------------------------
     def process_data_dict(self, data, keep_pinned=False):

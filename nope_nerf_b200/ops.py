@@ -124,14 +124,15 @@ class RenderCall:
         nbytes = L.lib.nnb_workspace_bytes(N, S, flags, engine)
         self.ws = _pool.take(nbytes, dev)
         a.workspace = L.ptr(self.ws); a.workspace_bytes = self.ws.numel()
-        self.args = a; self.N = N; self.S = S; self.stash = stash
+        self.args = a; self.N = N; self.S = S; self.stash = stash; self.pooled = True
         L.check(L.lib.nnb_render_fwd(C.byref(a), _stream()), "nnb_render_fwd")
         if not stash:
             self.release()
 
     def release(self):
         if self.ws is not None:
-            _pool.give(self.ws); self.ws = None
+            if self.pooled: _pool.give(self.ws)
+            self.ws = None
 
     def backward(self, g_rgb, g_depth_pred, g_depth_gt, g_weights, g_c2w, g_cam=None, g_depth=None, g_scale_shift=None):
         """all outputs are accumulated into (caller-zeroed) buffers; g_weights may be None (pose only)."""
@@ -267,3 +268,38 @@ def chamfer(X, Y):
 def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     L.check(L.lib.nnb_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), int(step), float(lr), beta1, beta2, eps,
                                 _stream()), "nnb_adam_step")
+
+
+# ---- CUDA-graph friendly variants (device-resident per-step scalars) -----------------------------------------
+def pose_fwd_dev(r, t, init, cam_idx_dev, out):
+    L.check(L.lib.nnb_pose_fwd_dev(L.ptr(r), L.ptr(t), L.ptr(init), L.ptr(cam_idx_dev), L.ptr(out), _stream()), "nnb_pose_fwd_dev")
+
+
+def pose_bwd_dev(r, t, init, cam_idx_dev, g_c2w, g_r, g_t):
+    L.check(L.lib.nnb_pose_bwd_dev(L.ptr(r), L.ptr(t), L.ptr(init), L.ptr(cam_idx_dev), L.ptr(g_c2w), L.ptr(g_r), L.ptr(g_t), _stream()),
+            "nnb_pose_bwd_dev")
+
+
+def distortion_fwd_dev(scales, shifts, cam_idx_dev, fix_last, out2):
+    L.check(L.lib.nnb_distortion_fwd_dev(L.ptr(scales), L.ptr(shifts), scales.shape[0], L.ptr(cam_idx_dev), int(bool(fix_last)), L.ptr(out2),
+                                         _stream()), "nnb_distortion_fwd_dev")
+
+
+def distortion_bwd_dev(scales, cam_idx_dev, fix_last, g_ss, g_scales, g_shifts):
+    L.check(L.lib.nnb_distortion_bwd_dev(L.ptr(scales), scales.shape[0], L.ptr(cam_idx_dev), int(bool(fix_last)), L.ptr(g_ss), L.ptr(g_scales),
+                                         L.ptr(g_shifts), _stream()), "nnb_distortion_bwd_dev")
+
+
+def adam_step_dev(p, g, m, v, step_dev, lr_dev, beta1=0.9, beta2=0.999, eps=1e-8):
+    L.check(L.lib.nnb_adam_step_dev(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), L.ptr(step_dev), L.ptr(lr_dev), beta1, beta2, eps,
+                                    _stream()), "nnb_adam_step_dev")
+
+
+def counter_incr(counters):
+    L.check(L.lib.nnb_counter_incr(L.ptr(counters), counters.numel(), _stream()), "nnb_counter_incr")
+
+
+def loss_rgb_depth_indirect(rgb, depth_pred, depth_gt, mask, w_rgb, w_depth, rgb_l2, img_pp, ray_idx, HW, out, g_rgb, g_dp, g_dg, grad_scale=1.0):
+    L.check(L.lib.nnb_loss_rgb_depth_indirect(L.ptr(rgb), L.ptr(img_pp), L.ptr(ray_idx), int(HW), L.ptr(depth_pred), L.ptr(depth_gt), L.ptr(mask),
+                                              rgb.shape[0], float(w_rgb), float(w_depth), int(bool(rgb_l2)), float(grad_scale), L.ptr(out),
+                                              L.ptr(g_rgb), L.ptr(g_dp), L.ptr(g_dg), _stream()), "nnb_loss_rgb_depth_indirect")
