@@ -269,7 +269,8 @@ class _GraphStep:
             if self.graph is None:
                 torch.cuda.synchronize()
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
+                # thread_local: the NCCL watchdog thread may touch the CUDA API while this thread captures
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                     self.body()
             self.graph.replay()
         for fa in fas:
@@ -331,6 +332,8 @@ class Trainer(object):
         self._fadam = {}
         # whole-step CUDA graph for render-only steps (statistically, not stream-, identical pixel/jitter draws)
         self.use_cuda_graph = kwargs.get('use_cuda_graph', os.environ.get('NNB_CUDA_GRAPH', '1') == '1')
+        if self.world > 1 and os.environ.get('NNB_GRAPH_DP', '0') != '1':
+            self.use_cuda_graph = False      # NCCL inside a captured graph is opt-in (NNB_GRAPH_DP=1); eager sequence otherwise
         self._gsteps = {}
 
     # ------------------------------------------------------------------------------------
