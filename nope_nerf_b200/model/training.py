@@ -182,6 +182,10 @@ class _GraphStep:
         return all(fa.ok for fa in self._adams())
 
     def body(self):
+        self.body_a(); self.reduce(); self.body_b()
+
+    def body_a(self):
+        """everything up to the local gradients"""
         tr = self.tr; dev = tr.device
         pose, dnet = tr.pose_param_net, tr.distortion_net
         net = tr.model.renderer.model; rend = tr.model.renderer
@@ -221,9 +225,17 @@ class _GraphStep:
                                gv['scales'] if dnet.global_scales.requires_grad else None,
                                gv['shifts'] if dnet.global_shifts.requires_grad else None)
         gv['losses'].copy_(self.out4 * gs if tr.world > 1 else self.out4)
+
+    def reduce(self):
+        tr = self.tr
         if tr.world > 1:
-            torch.distributed.all_reduce(gbuf, group=tr.dp_group)
-        # optimizers: device-side step counters / learning rates
+            torch.distributed.all_reduce(tr._gbuf, group=tr.dp_group)
+
+    def body_b(self):
+        """optimizers: device-side step counters / learning rates"""
+        tr = self.tr
+        gbuf = tr._gbuf
+        net = tr.model.renderer.model
         ops.counter_incr(self.steps)
         fa_m, fa_p, fa_d = self._adams()
         gm = tr.optimizer.param_groups[0]; b1, b2 = gm['betas']
@@ -268,11 +280,22 @@ class _GraphStep:
         else:
             if self.graph is None:
                 torch.cuda.synchronize()
+                # world == 1: one graph for the whole step.  world > 1: the NCCL all-reduce stays an eager call between two
+                # graphs (gradients | optimizers); thread_local because the NCCL watchdog thread touches the CUDA API
                 self.graph = torch.cuda.CUDAGraph()
-                # thread_local: the NCCL watchdog thread may touch the CUDA API while this thread captures
-                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                    self.body()
+                if tr.world == 1:
+                    with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                        self.body()
+                else:
+                    with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                        self.body_a()
+                    self.graph_b = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph_b, capture_error_mode="thread_local"):
+                        self.body_b()
             self.graph.replay()
+            if tr.world > 1:
+                self.reduce()
+                self.graph_b.replay()
         for fa in fas:
             fa.nsteps += 1; fa._synced = False
         self.steps_host = [fa.nsteps for fa in fas]
@@ -332,8 +355,8 @@ class Trainer(object):
         self._fadam = {}
         # whole-step CUDA graph for render-only steps (statistically, not stream-, identical pixel/jitter draws)
         self.use_cuda_graph = kwargs.get('use_cuda_graph', os.environ.get('NNB_CUDA_GRAPH', '1') == '1')
-        if self.world > 1 and os.environ.get('NNB_GRAPH_DP', '0') != '1':
-            self.use_cuda_graph = False      # NCCL inside a captured graph is opt-in (NNB_GRAPH_DP=1); eager sequence otherwise
+        if self.world > 1 and os.environ.get('NNB_GRAPH_DP', '1') != '1':
+            self.use_cuda_graph = False      # data parallel: two graphs around an eager NCCL all-reduce (NNB_GRAPH_DP=0 disables)
         self._gsteps = {}
 
     # ------------------------------------------------------------------------------------
