@@ -65,6 +65,9 @@ typedef struct nnb_render_args {
   float* alpha;      /* [N,S] or NULL */
   void* workspace;
   size_t workspace_bytes;
+  /* explicit-point field queries (nnb_field_fwd/bwd only; NULL for rendering): OfficialStaticNerf.forward(p, ray_d) */
+  const float* pts;  /* [N,3] */
+  const float* dirs; /* [N,3] or NULL (-> ones, like use_ray_dir = False) */
 } nnb_render_args;
 
 typedef struct nnb_render_bwd_args {
@@ -93,6 +96,12 @@ int nnb_debug_layout(int32_t N, int32_t S, uint32_t flags, int32_t engine, size_
 /* bytes of workspace needed by nnb_render_fwd (+bwd when NNB_STASH) */
 size_t nnb_workspace_bytes(int32_t N, int32_t S, uint32_t flags, int32_t engine);
 int nnb_render_fwd(const nnb_render_args* a, void* stream);
+/* OfficialStaticNerf.forward(p, ray_d, return_addocc=True) on explicit points (model/official_nerf.py:69-96), exact-fp32
+ * engine.  Uses a->pts/dirs, N points (S is ignored), weights, flags (NNB_DIST_ALPHA / NNB_SOFTPLUS / NNB_STASH) and the
+ * workspace; out_rgba [N,4] = (r,g,b, alpha-or-sigma).  nnb_field_bwd: g_rgba [N,4] -> g_pts [N,4], g_dirs [N,4] (xyz used),
+ * g_weights (+=, may be NULL). */
+int nnb_field_fwd(const nnb_render_args* a, float* out_rgba, void* stream);
+int nnb_field_bwd(const nnb_render_args* a, const float* g_rgba, float* g_pts, float* g_dirs, float* g_weights, void* stream);
 int nnb_render_bwd(const nnb_render_bwd_args* a, void* stream);
 
 /* LearnPose.forward (model/poses.py:23-31): c2w = [Exp(r[id]) t[id]; 0 1] @ init_c2w[id] */

@@ -22,7 +22,7 @@ class RenderArgs(C.Structure):
                 ("N", C.c_int32), ("S", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("h_d", C.c_int32), ("w_d", C.c_int32),
                 ("near_", C.c_float), ("far_", C.c_float), ("flags", C.c_uint32), ("engine", C.c_int32),
                 ("rgb", _f), ("depth_pred", _f), ("depth_gt", _f), ("mask", _f), ("z_vals", _f), ("alpha", _f),
-                ("workspace", _f), ("workspace_bytes", C.c_size_t)]
+                ("workspace", _f), ("workspace_bytes", C.c_size_t), ("pts", _f), ("dirs", _f)]
 
 
 class RenderBwdArgs(C.Structure):
@@ -42,6 +42,8 @@ def _load():
     lib.nnb_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_uint32, C.c_int32]
     lib.nnb_render_fwd.argtypes = [C.POINTER(RenderArgs), C.c_void_p]
     lib.nnb_render_bwd.argtypes = [C.POINTER(RenderBwdArgs), C.c_void_p]
+    lib.nnb_field_fwd.argtypes = [C.POINTER(RenderArgs), _f, C.c_void_p]
+    lib.nnb_field_bwd.argtypes = [C.POINTER(RenderArgs), _f, _f, _f, _f, C.c_void_p]
     lib.nnb_pose_fwd.argtypes = [_f, _f, _f, C.c_int32, _f, C.c_void_p]
     lib.nnb_pose_bwd.argtypes = [_f, _f, _f, C.c_int32, _f, _f, _f, C.c_void_p]
     lib.nnb_loss_rgb_depth.argtypes = [_f, _f, _f, _f, C.c_int32, _f, _f, _f, C.c_int32, C.c_float, C.c_float, C.c_int32,

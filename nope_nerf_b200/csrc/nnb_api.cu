@@ -7,6 +7,9 @@
 
 cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st);
 cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
+cudaError_t simt_field_fwd(const nnb_render_args& a, const WsLayout& L, float* out_rgba, cudaStream_t st);
+cudaError_t simt_field_bwd(const nnb_render_args& a, const WsLayout& L, const float* g_rgba, float* g_pts, float* g_dirs, float* g_weights,
+                           cudaStream_t st);
 #ifdef NNB_WITH_TC
 cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStream_t st);
 cudaError_t tc_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st);
@@ -116,6 +119,27 @@ int nnb_render_bwd(const nnb_render_bwd_args* b, void* stream) {
 #endif
   e = simt_render_bwd(*b, L, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_render_bwd");
+}
+
+static int check_field(const nnb_render_args* a) {
+  if (!a || !a->pts || !a->weights || a->N <= 0) return fail(-3, "nnb_field_*: need pts, weights, N > 0");
+  size_t need = make_layout(a->N, 1, a->flags, NNB_ENGINE_SIMT).total;
+  if (!a->workspace || a->workspace_bytes < need) return fail(-5, "workspace too small: have %zu need %zu", a->workspace_bytes, need);
+  return 0;
+}
+int nnb_field_fwd(const nnb_render_args* a, float* out_rgba, void* stream) {
+  int rc = check_field(a); if (rc) return rc;
+  if (!out_rgba) return fail(-3, "nnb_field_fwd: out_rgba is null");
+  nnb_render_args b = *a; b.S = 1; b.engine = NNB_ENGINE_SIMT;
+  cudaError_t e = simt_field_fwd(b, make_layout(b.N, 1, b.flags, NNB_ENGINE_SIMT), out_rgba, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_field_fwd");
+}
+int nnb_field_bwd(const nnb_render_args* a, const float* g_rgba, float* g_pts, float* g_dirs, float* g_weights, void* stream) {
+  int rc = check_field(a); if (rc) return rc;
+  if (!g_rgba || !(a->flags & NNB_STASH)) return fail(-3, "nnb_field_bwd: need g_rgba and a forward run with NNB_STASH");
+  nnb_render_args b = *a; b.S = 1; b.engine = NNB_ENGINE_SIMT;
+  cudaError_t e = simt_field_bwd(b, make_layout(b.N, 1, b.flags, NNB_ENGINE_SIMT), g_rgba, g_pts, g_dirs, g_weights, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_field_bwd");
 }
 
 int nnb_pose_fwd(const float* r, const float* t, const float* init, int32_t cam, float* c2w, void* stream) {

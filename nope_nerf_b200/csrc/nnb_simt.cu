@@ -112,6 +112,16 @@ __device__ __forceinline__ void tile_to_global(const float* s, int lds, float* g
   }
 }
 
+__device__ __forceinline__ void row_view_dir(const nnb_render_args& a, size_t m, size_t M, const Ray& ray, float v[3]) {
+  if (a.pts) {
+    size_t mm = m < M ? m : M - 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = a.dirs ? __ldg(a.dirs + 3 * mm + c) : 1.f;
+    return;
+  }
+  view_dir(a, ray, v);
+}
+
 struct SimtPtrs {
   SampleRec* rec;
   float *h[8], *feat, *hr, *enc, *denc;
@@ -122,6 +132,11 @@ struct SimtPtrs {
 __device__ __forceinline__ void row_geometry(const nnb_render_args& a, size_t m, size_t M, Ray& ray, int& n, int& i, float& z,
                                              float p[3]) {
   size_t mm = m < M ? m : M - 1;
+  if (a.pts) {   // explicit-point field query: no ray, the point is given
+    n = (int)mm; i = 0; z = 0.f;
+    p[0] = __ldg(a.pts + 3 * mm); p[1] = __ldg(a.pts + 3 * mm + 1); p[2] = __ldg(a.pts + 3 * mm + 2);
+    return;
+  }
   n = (int)(mm / a.S); i = (int)(mm % a.S);
   setup_ray(a, n, ray);
   z = sample_z(a, n, i);
@@ -188,7 +203,7 @@ __global__ void __launch_bounds__(256, 1) simt_mlp_fwd(nnb_render_args a, SimtPt
   if (tid < TM) {
     Ray ray; int n, i; float z, p[3], v[3];
     row_geometry(a, m0 + tid, M, ray, n, i, z, p);
-    view_dir(a, ray, v);
+    row_view_dir(a, m0 + tid, M, ray, v);
     float* de = oth + tid * LDB + 256;
     encode<4>(v, [&](int k, float val) { de[k] = val; });
 #pragma unroll
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(256, 1) simt_mlp_dgrad(nnb_render_args a, Simt
   if (tid < TM) {
     Ray ray; int n, i; float z, p[3], v[3], gvd[3];
     row_geometry(a, m0 + tid, M, ray, n, i, z, p);
-    view_dir(a, ray, v);
+    row_view_dir(a, m0 + tid, M, ray, v);
     const float* ge = bufB + tid * LDB + 256;
     encode_bwd<4>(v, [&](int k) { return ge[k]; }, gvd);
     P.gv[m0 + tid] = make_float4(gvd[0], gvd[1], gvd[2], 0.f);
@@ -624,6 +639,38 @@ cudaError_t simt_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStr
   return cudaGetLastError();
 }
 
+__global__ void rec_to_rgba(const SampleRec* rec, float4* out, size_t M) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) out[m] = make_float4(rec[m].r, rec[m].g, rec[m].b, rec[m].a);
+}
+
+cudaError_t simt_field_fwd(const nnb_render_args& a, const WsLayout& L, float* out_rgba, cudaStream_t st) {
+  SimtPtrs P = make_ptrs(L, a.workspace);
+  cudaError_t e0 = simt_init();
+  if (e0 != cudaSuccess) return e0;
+  int tiles = (int)((L.M + TM - 1) / TM);
+  simt_mlp_fwd<<<tiles, 256, FWD_SMEM, st>>>(a, P, L.M, (a.flags & NNB_STASH) ? 1 : 0);
+  rec_to_rgba<<<(unsigned)((L.M + 255) / 256), 256, 0, st>>>(P.rec, reinterpret_cast<float4*>(out_rgba), L.M);
+  return cudaGetLastError();
+}
+
+cudaError_t simt_wgrad_all(const SimtPtrs& P, const WsLayout& L, float* gw, cudaStream_t st);
+
+cudaError_t simt_field_bwd(const nnb_render_args& a, const WsLayout& L, const float* g_rgba, float* g_pts, float* g_dirs, float* g_weights,
+                           cudaStream_t st) {
+  SimtPtrs P = make_ptrs(L, a.workspace);
+  cudaError_t e = simt_init();
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(P.gs, g_rgba, L.M * 16, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return e;
+  int tiles = (int)((L.M + TM - 1) / TM);
+  simt_mlp_dgrad<<<tiles, 256, BWD_SMEM, st>>>(a, P, L.M, g_weights ? 1 : 0);
+  if (g_weights) { e = simt_wgrad_all(P, L, g_weights, st); if (e != cudaSuccess) return e; }
+  if (g_pts) { e = cudaMemcpyAsync(g_pts, P.gp, L.M * 16, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; }
+  if (g_dirs) { e = cudaMemcpyAsync(g_dirs, P.gv, L.M * 16, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_simt_wgrad_jobs(const SmallJob* jobs, int njobs, size_t M, cudaStream_t st) {
   WJobs J{}; int tile = 0;
   for (int i = 0; i < njobs && i < 16; ++i) {
@@ -651,20 +698,8 @@ cudaError_t launch_ray_bwd(const nnb_render_bwd_args& b, const SampleRec* recs, 
   return cudaGetLastError();
 }
 
-cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st) {
-  const nnb_render_args& a = b.fwd;
-  SimtPtrs P = make_ptrs(L, a.workspace);
-  cudaError_t e0 = simt_init();
-  if (e0 != cudaSuccess) return e0;
-  int tiles = (int)((L.M + TM - 1) / TM);
-  nnb_prof_mark(st);
-  composite_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gs, nullptr);
-  nnb_prof_mark(st);
-  const int write_dy = b.g_weights ? 1 : 0;
-  simt_mlp_dgrad<<<tiles, 256, BWD_SMEM, st>>>(a, P, L.M, write_dy);
-  nnb_prof_mark(st);
-  if (b.g_weights) {
-    float* gw = b.g_weights;
+cudaError_t simt_wgrad_all(const SimtPtrs& P, const WsLayout& L, float* gw, cudaStream_t st) {
+  {
     WJobs J{}; int nj = 0, tile = 0;
     auto add = [&](const float* dY, int ldy, int Nn, const float* X, int ldx, int Kk, float* dW, int ldw, float* db) {
       WJob& j = J.j[nj++];
@@ -685,6 +720,22 @@ cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cud
     int msplit = (int)((L.M + 4095) / 4096); if (msplit < 1) msplit = 1; if (msplit > 16) msplit = 16;
     simt_wgrad<<<dim3(tile, msplit), 256, 0, st>>>(J, L.M, msplit);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t simt_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st) {
+  const nnb_render_args& a = b.fwd;
+  SimtPtrs P = make_ptrs(L, a.workspace);
+  cudaError_t e0 = simt_init();
+  if (e0 != cudaSuccess) return e0;
+  int tiles = (int)((L.M + TM - 1) / TM);
+  nnb_prof_mark(st);
+  composite_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gs, nullptr);
+  nnb_prof_mark(st);
+  const int write_dy = b.g_weights ? 1 : 0;
+  simt_mlp_dgrad<<<tiles, 256, BWD_SMEM, st>>>(a, P, L.M, write_dy);
+  nnb_prof_mark(st);
+  if (b.g_weights) { cudaError_t ew = simt_wgrad_all(P, L, b.g_weights, st); if (ew != cudaSuccess) return ew; }
   nnb_prof_mark(st);
   ray_bwd<<<(a.N + 7) / 8, 256, 0, st>>>(b, P.rec, P.gp, P.gv);
   nnb_prof_mark(st);

@@ -11,4 +11,5 @@ from .intrinsics import LearnFocal
 from .eval_pose_one_epoch import Trainer_pose
 from .distortions import Learn_Distortion
 from .losses import Loss, Loss_Eval
+from .extracting_images import Extract_Images
 from . import common

@@ -373,3 +373,100 @@ def test_cuda_graph_step_matches_eager_sequence():
     _report("cuda_graph", loss_eager_last=le[-1], loss_graph_last=lg[-1], dparam=np.abs(res[False][1] - res[True][1]).max())
     assert abs(le[0] - lg[0]) < 1e-5 * abs(le[0])                      # first call is eager in both modes
     assert np.abs(lg - le).max() < 0.15 * np.abs(le).max(), (le, lg)   # later draws may differ (graph-safe philox offsets)
+
+
+def test_full_frame_renderer_vs_reference_golden():
+    """Extract_Images.render_frame (config 4 caller, model/extracting_images.py:52-77): the whole 27x48 frame in one call;
+    the golden's 32 rays (eval mode, ones prior, init_c2w pose) must come out identical."""
+    import nope_nerf_b200.model as mdl
+    from nope_nerf_b200 import ops
+    from _cfg import default_cfg
+    g = load_golden("render_eval_ones")
+    cfg = default_cfg(); cfg["rendering"]["num_points"] = int(g["S"]); cfg["extract_images"] = {"resolution": (int(g["H"]), int(g["W"]))}
+    dev = torch.device("cuda")
+    for eng in ("simt", "tc"):
+        ops.set_default_engine(eng)
+        net = mdl.OfficialStaticNerf(cfg)
+        net.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in O.init_params(seed=int(g["seed"])).items()})
+        rend = mdl.Renderer(net, cfg["rendering"], device=dev)
+        ex = mdl.Extract_Images(rend, cfg, device=dev, render_type="nope_nerf")
+        cam = torch.diag(torch.tensor([float(g["kx"]), float(g["ky"]), -1.0, 1.0])).to(dev)
+        rgb, depth = ex.render_frame(cuda(g["c2w"]), cam, int(g["H"]), int(g["W"]))
+        idx = g["ray_idx"]
+        e_rgb = relmax(rgb.reshape(-1, 3).cpu().numpy()[idx], g["rgb"]); e_d = relmax(depth.reshape(-1).cpu().numpy()[idx], g["depth_pred"])
+        _report("full_frame/%s" % eng, rgb=e_rgb, depth=e_d)
+        assert e_rgb < 1e-4 and e_d < 1e-4, (eng, e_rgb, e_d)
+        # row-block sharding (multi-GPU frame rendering) reproduces the same pixels
+        top, _ = ex.render_frame(cuda(g["c2w"]), cam, int(g["H"]), int(g["W"]), rows=(0, 13))
+        bot, _ = ex.render_frame(cuda(g["c2w"]), cam, int(g["H"]), int(g["W"]), rows=(13, int(g["H"])))
+        assert torch.equal(torch.cat([top, bot], 0), rgb)
+
+
+def test_trainer_pose_vs_oracle(monkeypatch):
+    """Trainer_pose (model/eval_pose_one_epoch.py:62-98): frozen field, eval mode, ones prior, F.mse_loss; pose gradients only."""
+    import nope_nerf_b200.model as mdl
+    from nope_nerf_b200 import ops
+    from _cfg import default_cfg
+    H, W, V, N, S = 30, 40, 4, 64, 64
+    rng = np.random.default_rng(5)
+    cfg = default_cfg(); cfg["rendering"]["num_points"] = S; cfg["eval_pose"]["n_points"] = N
+    dev = torch.device("cuda")
+    P = O.init_params(seed=13)
+    r0 = rng.normal(0, .05, (V, 3)).astype(np.float32); t0 = rng.normal(0, .05, (V, 3)).astype(np.float32)
+    img = rng.uniform(0, 1, (3, H, W)).astype(np.float32)
+    ray_idx = rng.permutation(H * W)[:N]
+    kx, ky = 1.2, -1.6
+    # oracle
+    ocfg = dict(O.DEFAULT_CFG); ocfg["num_points"] = S
+    c2w = O.make_c2w(r0[2].astype(np.float64), t0[2].astype(np.float64))
+    P64 = {k: v.astype(np.float64) for k, v in P.items()}
+    pix = O.pixels_from_idx(ray_idx, H, W, np.float64)
+    out, cache = O.render_forward(P64, pix, np.ones(N), c2w, kx, ky, ocfg, noise=None, eval_=True)
+    gt = img.reshape(3, -1)[:, ray_idx].T.astype(np.float64)
+    loss = ((out["rgb"] - gt) ** 2).mean()
+    gr = O.render_backward(P64, cache, 2 * (out["rgb"] - gt) / (3 * N), np.zeros(N), np.zeros(N))
+    g_r, g_t = O.make_c2w_bwd(r0[2].astype(np.float64), t0[2].astype(np.float64), None, gr["c2w"])
+    for eng in ("simt", "tc"):
+        ops.set_default_engine(eng)
+        net = mdl.OfficialStaticNerf(cfg)
+        net.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in P.items()})
+        model = mdl.get_model(mdl.Renderer(net, cfg["rendering"], device=dev), cfg, device=dev)
+        pose = mdl.LearnPose(V, True, True, cfg).to(dev)
+        with torch.no_grad():
+            pose.r.copy_(cuda(r0)); pose.t.copy_(cuda(t0))
+        opt = torch.optim.Adam(pose.parameters(), lr=1e-3)
+        tp = mdl.Trainer_pose(model, cfg["eval_pose"], device=dev, optimizer_pose=opt, pose_param_net=pose)
+        monkeypatch.setattr(torch, "randperm", lambda n, device=None: cuda(ray_idx))
+        cam = torch.tensor([[kx, 0, 0, 0], [0, ky, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], dtype=torch.float32)[None]
+        data = {"img": torch.from_numpy(img)[None], "img.idx": torch.tensor([2]), "img.camera_mat": cam, "img.scale_mat": torch.eye(4)[None]}
+        w_before = net.flat_weights().clone()
+        ld = tp.train_step(data)
+        e = dict(loss=abs(ld["loss"].item() - loss) / loss, g_r=relmax(pose.r.grad.cpu().numpy()[2], g_r), g_t=relmax(pose.t.grad.cpu().numpy()[2], g_t))
+        _report("trainer_pose/%s" % eng, **e)
+        assert e["loss"] < 1e-5 and e["g_r"] < 2e-4 and e["g_t"] < 2e-4, (eng, e)
+        assert torch.equal(net.flat_weights(), w_before)               # the field stays frozen
+        assert float(pose.r.grad.abs().sum() - pose.r.grad[2].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("name", ["mlp_alpha_softplus", "mlp_sigma_relu"])
+def test_field_forward_on_points_vs_reference_golden(name):
+    """OfficialStaticNerf.forward(p, ray_d, return_addocc=True) + autograd (model/official_nerf.py:69-96)."""
+    import nope_nerf_b200.model as mdl
+    from _cfg import default_cfg
+    g = load_golden(name)
+    cfg = default_cfg(); cfg["rendering"]["dist_alpha"] = bool(g["dist_alpha"]); cfg["model"]["occ_activation"] = str(g["occ"])
+    net = mdl.OfficialStaticNerf(cfg)
+    net.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in O.init_params(seed=int(g["seed"])).items()})
+    net = net.cuda()
+    tp = cuda(g["pts"]).requires_grad_(True); td = cuda(g["dirs"]).requires_grad_(True)
+    rgb, a = net(tp, td, return_addocc=True)
+    assert rgb.shape == (tp.shape[0], 3) and a.shape == (tp.shape[0], 1)
+    ((rgb * cuda(g["g_rgb"])).sum() + (a[:, 0] * cuda(g["g_a"])).sum()).backward()
+    floor = 2e-2 if str(g["occ"]) == "relu" else 1e-4
+    e = dict(rgb=relmax(rgb.detach().cpu().numpy(), g["rgb"]), a=relmax(a.detach().cpu().numpy()[:, 0], g["a"]),
+             g_pts=relmax(tp.grad.cpu().numpy(), g["g_pts"]), g_dirs=relmax(td.grad.cpu().numpy(), g["g_dirs"]),
+             g_params=check_param_digest(g, {n: p.grad.cpu().numpy() for n, p in net.named_parameters()}))
+    _report("field/%s" % name, **e)
+    assert e["rgb"] < 1e-4 and e["a"] < 1e-4
+    assert e["g_pts"] < max(floor, 2e-4) and e["g_dirs"] < max(floor, 2e-4) and e["g_params"] < max(floor, 5e-4), e
+    assert net(tp.detach(), only_occupancy=True).shape == (tp.shape[0], 1)
