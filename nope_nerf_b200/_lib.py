@@ -57,6 +57,7 @@ def _load():
     lib.nnb_distortion_bwd_dev.argtypes = [_f, C.c_int32, _f, C.c_int32, _f, _f, _f, C.c_void_p]
     lib.nnb_adam_step_dev.argtypes = [_f, _f, _f, _f, C.c_int64, _f, _f, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.nnb_counter_incr.argtypes = [_f, C.c_int32, C.c_void_p]
+    lib.nnb_sample_pixels.argtypes = [_f, C.c_int32, C.c_int32, _f, C.c_void_p]
     lib.nnb_loss_rgb_depth_indirect.argtypes = [_f, _f, _f, C.c_int32, _f, _f, _f, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, _f, _f,
                                                 _f, _f, C.c_void_p]
     for name in ("nnb_refstage_fwd", "nnb_refstage_bwd"):

@@ -22,6 +22,7 @@ cudaError_t launch_distortion_fwd(const float*, const float*, int, const int*, i
 cudaError_t launch_distortion_bwd(const float*, int, const int*, int, const float*, float*, float*, cudaStream_t);
 cudaError_t launch_adam_dev(float*, const float*, float*, float*, int64_t, const int*, const float*, float, float, float, cudaStream_t);
 cudaError_t launch_incr(int*, int, cudaStream_t);
+cudaError_t launch_sample_pixels(const float*, int, int, long long*, cudaStream_t);
 cudaError_t launch_loss(const float*, const float*, const float*, const float* const*, const int64_t*, int, const float*, const float*, const uint8_t*,
                         int, float, float, int, float, float*, float*, float*, float*, cudaStream_t);
 cudaError_t launch_chamfer(const float*, int, const float*, int, int*, int*, float*, float, float*, float*, cudaStream_t);
@@ -173,6 +174,11 @@ int nnb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
   if (!p || !g || !m || !v || n <= 0 || !step_dev || !lr_dev) return fail(-3, "nnb_adam_step_dev: bad arguments");
   cudaError_t e = launch_adam_dev(p, g, m, v, n, step_dev, lr_dev, b1, b2, eps, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_adam_step_dev");
+}
+int nnb_sample_pixels(const float* u2n, int32_t HW, int32_t N, int64_t* out, void* stream) {
+  if (!u2n || !out || HW <= 0 || N <= 0 || N > HW / 2 || N > 12800) return fail(-3, "nnb_sample_pixels: bad arguments (need 0 < N <= min(HW/2, 12800))");
+  cudaError_t e = launch_sample_pixels(u2n, HW, N, reinterpret_cast<long long*>(out), (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_sample_pixels");
 }
 int nnb_counter_incr(int32_t* counters, int32_t n, void* stream) {
   if (!counters || n <= 0 || n > 32) return fail(-3, "nnb_counter_incr: bad arguments");

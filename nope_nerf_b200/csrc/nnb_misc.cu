@@ -192,6 +192,39 @@ __global__ void adam_dev_k(float* p, const float* g, float* m, float* v, int64_t
 }
 __global__ void incr_k(int* a, int n) { if (threadIdx.x < n) a[threadIdx.x] += 1; }
 
+// N distinct pixel ids uniformly from [0, HW): rejection sampling against a shared-memory hash set.
+// u holds 2N uniforms in [0,1) (torch.rand); same distribution as torch.randperm(HW)[:N] (training.py:257) at a
+// fraction of its cost (randperm sorts all HW keys).
+__global__ void sample_pixels_k(const float* __restrict__ u, int HW, int N, int tsize, long long* __restrict__ out) {
+  extern __shared__ int table[];   // open addressing, empty = -1
+  for (int i = threadIdx.x; i < tsize; i += blockDim.x) table[i] = -1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    int cand = 0; bool done = false;
+    for (int attempt = 0; attempt < 2 && !done; ++attempt) {
+      cand = min(HW - 1, (int)(u[i + attempt * N] * (float)HW));
+      unsigned h = ((unsigned)cand * 2654435761u) & (unsigned)(tsize - 1);
+      while (true) {
+        int prev = atomicCAS(&table[h], -1, cand);
+        if (prev == -1) { done = true; break; }
+        if (prev == cand) break;                       // duplicate -> redraw
+        h = (h + 1) & (unsigned)(tsize - 1);
+      }
+    }
+    while (!done) {                                    // (probability ~ (N/HW)^2) walk to the next free id
+      cand = (cand + 1) % HW;
+      unsigned h = ((unsigned)cand * 2654435761u) & (unsigned)(tsize - 1);
+      while (true) {
+        int prev = atomicCAS(&table[h], -1, cand);
+        if (prev == -1) { done = true; break; }
+        if (prev == cand) break;
+        h = (h + 1) & (unsigned)(tsize - 1);
+      }
+    }
+    out[i] = cand;
+  }
+}
+
 __global__ void adam_k(float* p, const float* g, float* m, float* v, int64_t n, float lr_bc1, float rsqrt_bc2, float b1, float b2, float eps) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -220,6 +253,14 @@ cudaError_t launch_distortion_bwd(const float* sc, int V, const int* cam_dev, in
 cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, const float* lr_dev, float b1, float b2,
                             float eps, cudaStream_t st) {
   adam_dev_k<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, step_dev, lr_dev, b1, b2, eps); return cudaGetLastError();
+}
+cudaError_t launch_sample_pixels(const float* u, int HW, int N, long long* out, cudaStream_t st) {
+  int tsize = 1024; while (tsize < 4 * N) tsize <<= 1;
+  if (tsize * 4 > 200 * 1024) return cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(sample_pixels_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  sample_pixels_k<<<1, 1024, tsize * 4, st>>>(u, HW, N, tsize, out);
+  return cudaGetLastError();
 }
 cudaError_t launch_incr(int* a, int n, cudaStream_t st) { incr_k<<<1, 32, 0, st>>>(a, n); return cudaGetLastError(); }
 cudaError_t launch_loss(const float* rgb, const float* rgb_gt, const float* img, const float* const* img_pp, const int64_t* ray_idx, int HW,

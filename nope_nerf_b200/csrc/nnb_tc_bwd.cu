@@ -172,12 +172,13 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           const uint32_t b_lbo = N * 16;
           const uint32_t aver = (uint32_t)t * 10u + (uint32_t)c_pos_aver[pos];
           uint32_t acc = 0;
+          uint32_t full_ok = mbar_probe(BAR(D_FULL + slot), phase);   // probe early: the barrier round trip hides under the other waits
           for (int ks = 0; ks < ksteps; ++ks) {
             if ((ks & 3) == 0 && pos != 6) {   // pos 6 re-reads the A version pos 5 already waited for
               mbar_wait(BAR(D_AREADY + (ks >> 2)), aver & 1u);
               tc_fence_after();
             }
-            mbar_wait(BAR(D_FULL + slot), phase);
+            if (!full_ok) mbar_wait(BAR(D_FULL + slot), phase);
             tc_fence_after();
             const uint32_t wb = smem_u32(smem + DG_W + slot * STAGE_BYTES);
             const uint64_t dAh = make_desc(a_hi + ks * 4096, 2048, 128), dAl = make_desc(a_lo + ks * 4096, 2048, 128);
@@ -186,6 +187,10 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
             tc_mma_f16(d_tmem, dAh, dBl, idesc, 1u);
             tc_mma_f16(d_tmem, dAh, dBh, idesc, 1u);
             acc = 1u;
+            {
+              const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
+              full_ok = mbar_probe(BAR(D_FULL + nslot), nphase);
+            }
             if (CL == 1) tc_commit(BAR(D_EMPTY + slot)); else tc_commit_mc(BAR(D_EMPTY + slot), cmask);
             if (++slot == NST) { slot = 0; phase ^= 1; }
           }
@@ -395,10 +400,18 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
       const uint32_t s0 = smem_u32(smem), ones = smem_u32(smem + WG_ONES);
       const uint32_t d_main = tmem_base, d_bias = tmem_base + 256;
       const uint32_t xsbo = big ? 2048u : 2048u;
-      uint32_t first = 0, gphase = 0;
+      uint32_t first = 0, gphase = 0, okm = 0;
       for (int t = t0; t < t1; ++t) {
         // products: (A_hi,B_hi) (A_hi,B_lo) (A_lo,B_hi); A = slot0 / slot5, B_hi = slot1(+2), B_lo = slot3(+4)
-        mbar_wait(BAR(G_FULL + 0), phase); mbar_wait(BAR(G_FULL + 1), phase); if (big) mbar_wait(BAR(G_FULL + 2), phase);
+        {   // probe all barriers of this tile back to back (their ~110-cycle round trips overlap), block only on the late ones
+          uint32_t ok[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ok[i] = mbar_probe(BAR(G_FULL + i), phase);
+          if (!ok[0]) mbar_wait(BAR(G_FULL + 0), phase);
+          if (!ok[1]) mbar_wait(BAR(G_FULL + 1), phase);
+          if (big && !ok[2]) mbar_wait(BAR(G_FULL + 2), phase);
+          okm = ok[3] | (ok[4] << 1) | (ok[5] << 2);
+        }
         tc_fence_after();
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t dA = make_desc(s0 + ks * 256, 128, 2048), dB = make_desc(s0 + WG_SLOT + ks * 256, 128, xsbo);
@@ -406,14 +419,15 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
           if (J.b_off >= 0) tc_mma_f16(d_bias, dA, make_desc(ones, 128, 256), idesc1, first | (uint32_t)(ks > 0));
         }
         first = 1u;
-        mbar_wait(BAR(G_FULL + 3), phase); if (big) mbar_wait(BAR(G_FULL + 4), phase);
+        if (!(okm & 1u)) mbar_wait(BAR(G_FULL + 3), phase);
+        if (big && !(okm & 2u)) mbar_wait(BAR(G_FULL + 4), phase);
         tc_fence_after();
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t dA = make_desc(s0 + ks * 256, 128, 2048), dB = make_desc(s0 + 3 * WG_SLOT + ks * 256, 128, xsbo);
           tc_mma_f16(d_main, dA, dB, idesc, 1u);
         }
         tc_commit(BAR(G_EMPTY + 0)); tc_commit(BAR(G_EMPTY + 3)); if (big) tc_commit(BAR(G_EMPTY + 4));
-        mbar_wait(BAR(G_FULL + 5), phase);
+        if (!(okm & 4u)) mbar_wait(BAR(G_FULL + 5), phase);
         tc_fence_after();
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t dA = make_desc(s0 + 5 * WG_SLOT + ks * 256, 128, 2048), dB = make_desc(s0 + WG_SLOT + ks * 256, 128, xsbo);

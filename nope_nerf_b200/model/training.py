@@ -195,7 +195,10 @@ class _GraphStep:
         g_c2w = self.small[:16].view(4, 4); g_ss = self.small[16:18]
         ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx, dnet.fix_scaleN, self.ss)
         n_points = tr.n_training_points
-        ray_idx = torch.randperm(h * w, device=dev)[:n_points]                    # training.py:257
+        if tr.pixel_sampler == 'randperm' or (tr.pixel_sampler == 'auto' and not tr.use_cuda_graph) or n_points > min(h * w // 2, 12800):
+            ray_idx = torch.randperm(h * w, device=dev)[:n_points]                # training.py:257 (reference RNG stream)
+        else:
+            ray_idx = ops.sample_pixels(h * w, n_points, dev)                     # same distribution, no 2M-key sort
         S = int(rend.cfg['num_points'])
         noise = None
         if rend.cfg['sample_option'] == 'uniform':
@@ -358,6 +361,9 @@ class Trainer(object):
         if self.world > 1 and os.environ.get('NNB_GRAPH_DP', '1') != '1':
             self.use_cuda_graph = False      # data parallel: two graphs around an eager NCCL all-reduce (NNB_GRAPH_DP=0 disables)
         self._gsteps = {}
+        # 'randperm' = the reference's torch.randperm(H*W)[:N] (identical RNG stream in eager mode); 'hash' = nnb_sample_pixels;
+        # 'auto' = randperm when running eagerly, hash inside the CUDA graph (whose RNG stream differs from eager anyway)
+        self.pixel_sampler = kwargs.get('pixel_sampler', 'auto')
 
     # ------------------------------------------------------------------------------------
     def _grad_buffer(self):

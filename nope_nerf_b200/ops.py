@@ -303,3 +303,11 @@ def loss_rgb_depth_indirect(rgb, depth_pred, depth_gt, mask, w_rgb, w_depth, rgb
     L.check(L.lib.nnb_loss_rgb_depth_indirect(L.ptr(rgb), L.ptr(img_pp), L.ptr(ray_idx), int(HW), L.ptr(depth_pred), L.ptr(depth_gt), L.ptr(mask),
                                               rgb.shape[0], float(w_rgb), float(w_depth), int(bool(rgb_l2)), float(grad_scale), L.ptr(out),
                                               L.ptr(g_rgb), L.ptr(g_dp), L.ptr(g_dg), _stream()), "nnb_loss_rgb_depth_indirect")
+
+
+def sample_pixels(hw, n, device):
+    """n distinct pixel ids uniform in [0, hw) (distribution of torch.randperm(hw)[:n])"""
+    u = torch.rand(2 * n, device=device)
+    out = torch.empty(n, dtype=torch.int64, device=device)
+    L.check(L.lib.nnb_sample_pixels(L.ptr(u), int(hw), int(n), L.ptr(out), _stream()), "nnb_sample_pixels")
+    return out

@@ -470,3 +470,18 @@ def test_field_forward_on_points_vs_reference_golden(name):
     assert e["rgb"] < 1e-4 and e["a"] < 1e-4
     assert e["g_pts"] < max(floor, 2e-4) and e["g_dirs"] < max(floor, 2e-4) and e["g_params"] < max(floor, 5e-4), e
     assert net(tp.detach(), only_occupancy=True).shape == (tp.shape[0], 1)
+
+
+def test_pixel_sampler_distinct_and_uniform():
+    from nope_nerf_b200 import ops
+    torch.manual_seed(0)
+    HW, N = 1080 * 1920, 1024
+    counts = torch.zeros(16, device="cuda")
+    for _ in range(50):
+        idx = ops.sample_pixels(HW, N, "cuda")
+        assert idx.min() >= 0 and idx.max() < HW and torch.unique(idx).numel() == N
+        counts += torch.bincount((idx * 16 // HW), minlength=16).float()
+    frac = (counts / counts.sum()).cpu().numpy()
+    assert np.abs(frac - 1 / 16).max() < 0.01            # 51 200 draws over 16 bins: sigma ~ 0.001
+    small = ops.sample_pixels(4096, 2048, "cuda")        # dense case exercises the duplicate / probing paths
+    assert torch.unique(small).numel() == 2048
