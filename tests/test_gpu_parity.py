@@ -354,7 +354,7 @@ def test_cuda_graph_step_matches_eager_sequence():
         opt = torch.optim.Adam(model.parameters(), lr=1e-3); opt_p = torch.optim.Adam(pose.parameters(), lr=5e-4)
         opt_d = torch.optim.Adam(dist.parameters(), lr=5e-4)
         tr = mdl.Trainer(model, opt, cfg["training"], device=dev, optimizer_pose=opt_p, pose_param_net=pose, optimizer_distortion=opt_d,
-                         distortion_net=dist, use_cuda_graph=mode)
+                         distortion_net=dist, use_cuda_graph=mode, pixel_sampler="hash")
         g = torch.Generator().manual_seed(3)
         frames = [dict(img=torch.rand(1, 3, H, W, generator=g).cuda(), dpt=(torch.rand(1, 24, 32, generator=g) * 6 + 0.6).cuda()) for _ in range(3)]
         cam = torch.tensor([[1.2, 0, 0, 0], [0, -1.6, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], dtype=torch.float32)[None]
