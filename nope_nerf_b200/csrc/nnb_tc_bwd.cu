@@ -42,7 +42,8 @@ __constant__ int c_pos_aver[N_POS] = {0, 1, 2, 3, 4, 5, 5, 6, 7, 8, 9};
 
 constexpr int DG_AHI = 0, DG_ALO = 65536, DG_W = 131072, DG_GENC = DG_W + NST * STAGE_BYTES;   // 180224
 constexpr int DG_SMALL = DG_GENC + 64 * 128 * 4;                                                   // 212992
-constexpr int DG_BAR = DG_SMALL + 640 * 4;
+constexpr int DG_COLSUM = DG_SMALL + 640 * 4;     // bias gradients: column sums of dY, [9 layers][256] fp32
+constexpr int DG_BAR = DG_COLSUM + 9 * 256 * 4;
 constexpr int DG_TOTAL = DG_BAR + 32 * 8 + 16;
 static_assert(DG_TOTAL <= 232448, "smem");
 enum { D_FULL = 0, D_EMPTY = NST, D_AREADY = 2 * NST, D_ACCFULL = 2 * NST + 4, D_ACCEMPTY = 2 * NST + 6 };
@@ -70,8 +71,30 @@ struct DgradPtrs {
   const float* hr; float* dyr; const uint32_t* mask;       // fp32 side stashes, ReLU bitmasks
   unsigned char* dyp[10];                                    // dY operand planes
   const unsigned int* gmax;                                  // max |g| bits -> power-of-two gradient scale
+  float* g_weights;                                          // flat gradient (bias gradients are reduced here), or NULL
   size_t Mpad;
 };
+
+// column sums over the 32 rows held by a warp: lane L ends up with sum_rows v[L]  (31 shuffles, butterfly transpose-reduce)
+__device__ __forceinline__ float warp_colsum32(const float* v, int lane) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float keep = (lane & 16) ? v[i + 16] : v[i], send = (lane & 16) ? v[i] : v[i + 16];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < off) {
+        const float keep = (lane & off) ? a[i + off] : a[i], send = (lane & off) ? a[i] : a[i + off];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return a[0];
+}
 
 // (GBF = false experiment: fp16 keeps a 22-bit hi/lo split only for |x| >~ 1, so the chain would run on
 // g * 2^k with the largest incoming cotangent at 2^8.  Gradients decay by ~5 orders of magnitude along the
@@ -99,6 +122,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_genc = reinterpret_cast<float*>(smem + DG_GENC);     // [64][128]
   float* s_small = reinterpret_cast<float*>(smem + DG_SMALL);   // W_rgb [3][128], w_sigma [256]
+  float* s_colsum = reinterpret_cast<float*>(smem + DG_COLSUM); // [9][256]: rows 0..7 = trunk layers, 8 = fc_feature
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DG_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DG_BAR + 32 * 8);
   const uint32_t bar0 = smem_u32(bars);
@@ -113,6 +137,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) s_colsum[i] = 0.f;
   for (int i = threadIdx.x; i < 640; i += blockDim.x)
     s_small[i] = (i < 384) ? __ldg(a.weights + nnb::W_RGB + i) : __ldg(a.weights + nnb::W_SIG + (i - 384));
   tc_fence_before();
@@ -282,6 +307,11 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
             for (int kb = 0; kb < 4; ++kb)
               split_g(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16);
             fence_async_smem(); mbar_arrive(BAR(D_AREADY + ci));
+            if (write_dy) {   // bias gradient of this layer: db[n] = sum_m dY[m][n] (off the MMA's critical path)
+              const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
+              const float cs = warp_colsum32(v, lane);
+              atomicAdd(&s_colsum[di * 256 + cb * 32 + lane], cs * inv_gscale);
+            }
           }
         }
         tc_fence_before();
@@ -309,6 +339,12 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   }
   tc_fence_before();
   __syncthreads();
+  if (write_dy && P.g_weights) {   // flush this CTA's bias-gradient partial sums
+    for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) {
+      const int di = i >> 8, n = i & 255;
+      atomicAdd(P.g_weights + (di < 8 ? nnb::b_off(di) : nnb::B_FEAT) + n, s_colsum[i]);
+    }
+  }
   if (CL > 1) cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
@@ -484,9 +520,11 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
 // gradient of rgb_layers.0[:, 256:283] only need G_ray[j] = sum_i g_yr[i][j]:
 //   dW[j][256+k] += G_ray[j] * denc_ray[k]   (block-reduced in shared memory, then one atomic per element)
 __global__ void ray_dir_grad(nnb_render_args a, const float* __restrict__ dyr, const float* __restrict__ denc, float4* __restrict__ gv,
-                             float* __restrict__ g_wdir /* gflat + W_RGBH + 256, row stride 283, or NULL */) {
+                             float* __restrict__ g_wdir /* gflat + W_RGBH + 256, row stride 283, or NULL */, float* __restrict__ g_bias_rgbh) {
   __shared__ float s_dw[128 * 27];
+  __shared__ float s_db[128];
   for (int i = threadIdx.x; i < 128 * 27; i += blockDim.x) s_dw[i] = 0.f;
+  if (threadIdx.x < 128) s_db[threadIdx.x] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const bool active = n < a.N;
@@ -498,6 +536,8 @@ __global__ void ray_dir_grad(nnb_render_args a, const float* __restrict__ dyr, c
       for (int q = 0; q < 4; ++q) G[q] += r[lane + 32 * q];
     }
     if (g_wdir) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(&s_db[lane + 32 * q], G[q]);     // rgb_layers.0 bias gradient = sum over all samples of g_yr
       const float* de = denc + (size_t)n * a.S * 32;
 #pragma unroll 1
       for (int k = 0; k < 27; ++k) {
@@ -508,8 +548,10 @@ __global__ void ray_dir_grad(nnb_render_args a, const float* __restrict__ dyr, c
     }
   }
   __syncthreads();
-  if (g_wdir)
+  if (g_wdir) {
     for (int i = threadIdx.x; i < 128 * 27; i += blockDim.x) atomicAdd(g_wdir + (size_t)(i / 27) * 283 + (i % 27), s_dw[i]);
+    if (threadIdx.x < 128) atomicAdd(g_bias_rgbh + threadIdx.x, s_db[threadIdx.x]);
+  }
   if (!active) return;
   float gd[27];
 #pragma unroll
@@ -619,7 +661,7 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   P.hr = reinterpret_cast<const float*>(base + L.hr); P.dyr = reinterpret_cast<float*>(base + L.dyr);
   P.mask = reinterpret_cast<const uint32_t*>(base + L.mask);
   for (int i = 0; i < 10; ++i) P.dyp[i] = reinterpret_cast<unsigned char*>(base + L.dyp[i]);
-  P.Mpad = L.Mpad; P.gmax = gmax;
+  P.Mpad = L.Mpad; P.gmax = gmax; P.g_weights = b.g_weights;
   const int n_tiles = (int)L.n_tiles;
   const int write_dy = b.g_weights ? 1 : 0;
   const int CL = cluster_size_option();
@@ -642,12 +684,12 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
       j.N = N; j.n_base = half * 128; j.ldw = ldw; j.kvalid = kvalid; j.w_off = w_off; j.b_off = b_off;
     };
     for (int half = 0; half < 2; ++half) {
-      add(0, 256, half, 0, 64, nnb::w_off(0), 63, 63, nnb::b_off(0));                      // layer 0: X = enc
-      for (int l = 1; l < 8; ++l) add(l, 256, half, l, 256, nnb::w_off(l), nnb::w_ld(l), 256, nnb::b_off(l));   // X = h[l-1] = xp[l]
+      add(0, 256, half, 0, 64, nnb::w_off(0), 63, 63, -1);                                 // layer 0: X = enc (biases: tc_dgrad)
+      for (int l = 1; l < 8; ++l) add(l, 256, half, l, 256, nnb::w_off(l), nnb::w_ld(l), 256, -1);   // X = h[l-1] = xp[l]
       add(4, 256, half, 0, 64, nnb::w_off(4) + 256, 319, 63, -1);                          // layer 4 enc slice
-      add(8, 256, half, 8, 256, nnb::W_FEAT, 256, 256, nnb::B_FEAT);                       // fc_feature: X = h7 = xp[8]
+      add(8, 256, half, 8, 256, nnb::W_FEAT, 256, 256, -1);                                // fc_feature: X = h7 = xp[8]
     }
-    add(9, 128, 0, 9, 256, nnb::W_RGBH, 283, 256, nnb::B_RGBH);                            // rgb_layers.0[:, :256]: X = feat
+    add(9, 128, 0, 9, 256, nnb::W_RGBH, 283, 256, -1);                                     // rgb_layers.0[:, :256]: X = feat (bias: ray_dir_grad)
     J.njobs = nj; J.n_tiles = n_tiles;
     int msplit = n_sm / nj; if (msplit < 1) msplit = 1; if (msplit > n_tiles) msplit = n_tiles;
     J.msplit = msplit;
@@ -665,7 +707,8 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   }
   nnb_prof_mark(st);
   ray_dir_grad<<<(a.N + 7) / 8, 256, 0, st>>>(a, reinterpret_cast<const float*>(base + L.dyr), reinterpret_cast<const float*>(base + L.denc), gv,
-                                              b.g_weights ? b.g_weights + nnb::W_RGBH + 256 : nullptr);
+                                              b.g_weights ? b.g_weights + nnb::W_RGBH + 256 : nullptr,
+                                              b.g_weights ? b.g_weights + nnb::B_RGBH : nullptr);
   e = launch_ray_bwd(b, recs, gp, gv, st);
   nnb_prof_mark(st);
   return e;
