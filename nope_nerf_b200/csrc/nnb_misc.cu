@@ -194,34 +194,61 @@ __global__ void incr_k(int* a, int n) { if (threadIdx.x < n) a[threadIdx.x] += 1
 
 // N distinct pixel ids uniformly from [0, HW): rejection sampling against a shared-memory hash set.
 // u holds 2N uniforms in [0,1) (torch.rand); same distribution as torch.randperm(HW)[:N] (training.py:257) at a
-// fraction of its cost (randperm sorts all HW keys).
+// fraction of its cost (randperm sorts all HW keys).  Deterministic for a given u: a duplicated candidate is kept by
+// the lowest ray index, first draws beat redraws, and the (very rare) leftovers are resolved serially.
+__device__ __forceinline__ int hs_claim(int* key, int* owner, int tsize, int cand, int who) {
+  unsigned h = ((unsigned)cand * 2654435761u) & (unsigned)(tsize - 1);
+  while (true) {
+    int prev = atomicCAS(&key[h], -1, cand);
+    if (prev == -1 || prev == cand) { atomicMin(&owner[h], who); return (int)h; }
+    h = (h + 1) & (unsigned)(tsize - 1);
+  }
+}
 __global__ void sample_pixels_k(const float* __restrict__ u, int HW, int N, int tsize, long long* __restrict__ out) {
-  extern __shared__ int table[];   // open addressing, empty = -1
-  for (int i = threadIdx.x; i < tsize; i += blockDim.x) table[i] = -1;
+  extern __shared__ int hs[];   // key[tsize] | owner[tsize] | pending list
+  int* key = hs; int* owner = hs + tsize; int* pend = owner + tsize; __shared__ int npend;
+  for (int i = threadIdx.x; i < tsize; i += blockDim.x) { key[i] = -1; owner[i] = 0x7fffffff; }
+  if (threadIdx.x == 0) npend = 0;
+  __syncthreads();
+  // round 1: first draw, ties -> lowest ray index
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    int cand = min(HW - 1, (int)(u[i] * (float)HW));
+    out[i] = ((long long)hs_claim(key, owner, tsize, cand, i) << 32) | (unsigned)cand;
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    int cand = 0; bool done = false;
-    for (int attempt = 0; attempt < 2 && !done; ++attempt) {
-      cand = min(HW - 1, (int)(u[i + attempt * N] * (float)HW));
-      unsigned h = ((unsigned)cand * 2654435761u) & (unsigned)(tsize - 1);
+    int slot = (int)(out[i] >> 32), cand = (int)(out[i] & 0xffffffffll);
+    out[i] = (owner[slot] == i) ? (long long)cand : -1ll;
+  }
+  __syncthreads();
+  // round 2: losers redraw; first-round winners always outrank them (who = N + i)
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    if (out[i] >= 0) continue;
+    int cand = min(HW - 1, (int)(u[i + N] * (float)HW));
+    out[i] = -2ll - (((long long)hs_claim(key, owner, tsize, cand, N + i) << 32) | (unsigned)cand);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    if (out[i] >= 0) continue;
+    long long enc = -2ll - out[i];
+    int slot = (int)(enc >> 32), cand = (int)(enc & 0xffffffffll);
+    if (owner[slot] == N + i) out[i] = cand;
+    else { int k = atomicAdd(&npend, 1); pend[k] = i; out[i] = -(long long)cand - 2; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && npend > 0) {   // leftovers (probability ~ (N/HW)^2 each): next free id, in ray order
+    for (int a = 1; a < npend; ++a) { int v = pend[a], b = a - 1; while (b >= 0 && pend[b] > v) { pend[b + 1] = pend[b]; --b; } pend[b + 1] = v; }
+    for (int k = 0; k < npend; ++k) {
+      int i = pend[k]; int cand = (int)(-(out[i] + 2));
       while (true) {
-        int prev = atomicCAS(&table[h], -1, cand);
-        if (prev == -1) { done = true; break; }
-        if (prev == cand) break;                       // duplicate -> redraw
-        h = (h + 1) & (unsigned)(tsize - 1);
+        cand = (cand + 1) % HW;
+        unsigned h = ((unsigned)cand * 2654435761u) & (unsigned)(tsize - 1);
+        bool found = false;
+        while (key[h] != -1) { if (key[h] == cand) { found = true; break; } h = (h + 1) & (unsigned)(tsize - 1); }
+        if (!found) { key[h] = cand; break; }
       }
+      out[i] = cand;
     }
-    while (!done) {                                    // (probability ~ (N/HW)^2) walk to the next free id
-      cand = (cand + 1) % HW;
-      unsigned h = ((unsigned)cand * 2654435761u) & (unsigned)(tsize - 1);
-      while (true) {
-        int prev = atomicCAS(&table[h], -1, cand);
-        if (prev == -1) { done = true; break; }
-        if (prev == cand) break;
-        h = (h + 1) & (unsigned)(tsize - 1);
-      }
-    }
-    out[i] = cand;
   }
 }
 
@@ -256,10 +283,11 @@ cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, int64_
 }
 cudaError_t launch_sample_pixels(const float* u, int HW, int N, long long* out, cudaStream_t st) {
   int tsize = 1024; while (tsize < 4 * N) tsize <<= 1;
-  if (tsize * 4 > 200 * 1024) return cudaErrorInvalidValue;
+  size_t smem = ((size_t)2 * tsize + N) * 4;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(sample_pixels_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  sample_pixels_k<<<1, 1024, tsize * 4, st>>>(u, HW, N, tsize, out);
+  sample_pixels_k<<<1, 1024, smem, st>>>(u, HW, N, tsize, out);
   return cudaGetLastError();
 }
 cudaError_t launch_incr(int* a, int n, cudaStream_t st) { incr_k<<<1, 32, 0, st>>>(a, n); return cudaGetLastError(); }
