@@ -290,11 +290,11 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         for (int kk = 0; kk < 4; ++kk) {
           const int kb = half * 4 + kk;
           split_store8(ee + kk * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
-          if (stash && !st.tcb) {
+          if (stash && !(st.tcb & 1)) {
             *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8) = make_float4(ee[kk * 8], ee[kk * 8 + 1], ee[kk * 8 + 2], ee[kk * 8 + 3]);
             *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8 + 4) = make_float4(ee[kk * 8 + 4], ee[kk * 8 + 5], ee[kk * 8 + 6], ee[kk * 8 + 7]);
           }
-          if (stash && st.tcb) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
+          if (stash && (st.tcb & 1)) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
             unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + row * 16;
             split_stream8_bf16(ee + kk * 8, dst + kb * 2048, dst + 16384 + kb * 2048);
           }
@@ -344,8 +344,9 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         PROF_ADD(1);
         const int nch = (g == 9) ? 2 : 4;                 // chunks of 32 columns handled by this half
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
-        const bool planes = stash && st.tcb;
-        unsigned char* xplane = (planes && g < 9) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + row * 16 : nullptr;
+        const bool planes = stash && (st.tcb & 1);
+        const int dbg = st.tcb >> 1;
+        unsigned char* xplane = (planes && g < 9 && !(dbg & 1)) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + row * 16 : nullptr;
         // pass 1 (critical path of the MMA warp): accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand, block by block.
         // The two halves convert adjacent 32-column chunks of the SAME 64-column block, so block `ci` is complete
         // after one chunk time.
@@ -408,11 +409,17 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
                 __stcs(reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4), make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
             }
             if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi|lo, coalesced 512 B per warp
+              if (dbg & 4) {
 #pragma unroll
-              for (int kb = 0; kb < 4; ++kb)
-                split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
+                for (int kb = 0; kb < 4; ++kb)
+                  split_store8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
+              } else {
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                  split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
+              }
             }
-            if (planes && g < 8) {   // ReLU bitmask of this 32-column chunk
+            if (planes && g < 8 && !(dbg & 2)) {   // ReLU bitmask of this 32-column chunk
               uint32_t mw = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
@@ -518,6 +525,7 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
   const int stash = (a.flags & NNB_STASH) ? 1 : 0;
   if (stash) {
     ts.tcb = (a.flags & NNB_TCBWD) ? 1 : 0;
+    if (ts.tcb) { const char* e = getenv("NNB_DBG_FWD"); if (e) ts.tcb |= atoi(e) << 1; }   // experiment knob (default off)
     for (int l = 0; l < 8; ++l) ts.h[l] = reinterpret_cast<float*>(base + L.h[l]);   // TCBWD: only h[7] is carved (others unused)
     ts.feat = reinterpret_cast<float*>(base + L.feat); ts.hr = reinterpret_cast<float*>(base + L.hr);
     ts.enc = reinterpret_cast<float*>(base + L.enc); ts.denc = reinterpret_cast<float*>(base + L.denc);
