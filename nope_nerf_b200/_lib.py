@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnope_nerf_b200.so")
+LIB_PATH = os.environ.get("NNB_LIB_PATH") or os.path.join(HERE, "libnope_nerf_b200.so")   # NNB_LIB_PATH: instrumented debug builds
 
 NUM_PARAMS = 595844
 DIST_ALPHA, NDC, NORMALISE, USE_DIR, WHITE_BG, EVAL, SOFTPLUS, SHIFT_FIRST, STASH, TCBWD = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512

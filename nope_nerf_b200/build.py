@@ -22,7 +22,11 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, tag=""):
+    """out/tag: build an instrumented variant (NNB_EXTRA_NVCC_FLAGS) beside the product library"""
+    global LIB
+    if out:
+        LIB = os.path.abspath(out)
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -33,7 +37,7 @@ def build(force=False, verbose=False):
     bdir = os.path.join(HERE, "build"); os.makedirs(bdir, exist_ok=True)
     procs = []
     for s in srcs:
-        o = os.path.join(bdir, os.path.basename(s) + ".o")
+        o = os.path.join(bdir, os.path.basename(s) + tag + ".o")
         objs.append(o)
         cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -52,4 +56,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out, tag=".dbg" if out else ""))

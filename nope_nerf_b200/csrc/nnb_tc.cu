@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8 + 4) = make_float4(ee[kk * 8 + 4], ee[kk * 8 + 5], ee[kk * 8 + 6], ee[kk * 8 + 7]);
           }
           if (stash && (st.tcb & 1)) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
-            unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + row * 16;
-            split_stream8_bf16(ee + kk * 8, dst + kb * 2048, dst + 16384 + kb * 2048);
+            unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + (row >> 6) * 8192 + (row & 63) * 16;   // [hi|lo][half][kb][64][8]
+            split_stream8_bf16(ee + kk * 8, dst + kb * 1024, dst + 16384 + kb * 1024);
           }
         }
       }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
         const bool planes = stash && (st.tcb & 1);
         const int dbg = st.tcb >> 1;
-        unsigned char* xplane = (planes && g < 9 && !(dbg & 1)) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + row * 16 : nullptr;
+        unsigned char* xplane = (planes && g < 9 && !(dbg & 1)) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
         // pass 1 (critical path of the MMA warp): accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand, block by block.
         // The two halves convert adjacent 32-column chunks of the SAME 64-column block, so block `ci` is complete
         // after one chunk time.
@@ -412,11 +412,11 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
               if (dbg & 4) {
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb)
-                  split_store8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
+                  split_store8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024);
               } else {
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb)
-                  split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 2048, xplane + 65536 + (cb * 4 + kb) * 2048);
+                  split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024);
               }
             }
             if (planes && g < 8 && !(dbg & 2)) {   // ReLU bitmask of this 32-column chunk

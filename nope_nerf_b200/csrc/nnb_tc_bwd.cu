@@ -5,12 +5,12 @@
 //              split-fp16 operands -> TMEM -> epilogue warps).  The epilogue applies the ReLU masks
 //              (bitmasks stashed by the forward), re-splits g_y into the next A operand IN PLACE and
 //              bulk-stores that shared-memory image as the dY operand plane of the weight-gradient pass.
-//   tc_wgrad : dW[n][k] = sum_m dY[m][n] X[m][k].  One CTA per (layer, 128-row half of n, sample split);
-//              the reduction runs over samples, so the stashed [feature/8][sample][8] planes are read as
-//              MN-major tcgen05 operands straight from bulk copies (no transposition anywhere);
-//              fp32 accumulation of the whole split stays in TMEM (128 lanes x 256 columns), bias
-//              gradients ride along as a 16-column MMA against a constant ones operand, and each CTA
-//              flushes its partial result once with red.global.add.
+//   tc_wgrad : dW[n][k] = sum_m dY[m][n] X[m][k].  CTA pairs walk an equal share of the (layer, tile) cost line,
+//              the two CTAs of a pair taking the two 128-row halves of dW (so the X plane is fetched from DRAM
+//              once and hits L2 the second time); the reduction runs over samples, so the stashed
+//              [sample half][feature/8][64 samples][8] planes are MN-major tcgen05 operands straight from bulk
+//              copies (no transposition anywhere), streamed through two 96 KB half-tile operand sets;
+//              fp32 accumulation stays in TMEM (running + total accumulator), one atomic flush per segment.
 //   small heads (fc_density, fc_rgb, the direction-encoding slice of rgb_layers.0) stay on the fp32
 //   SIMT wgrad kernel (0.3 % of the FLOPs); ray_dir_grad folds the per-ray direction gradient.
 #include "nnb_tc_common.cuh"
@@ -115,6 +115,31 @@ __device__ __forceinline__ void row_geometry_b(const nnb_render_args& a, size_t 
   sample_point(a, ray, z, p);
 }
 
+#ifdef NNB_TC_PROFILE
+__device__ unsigned long long g_wgprof[148][8];     // MMA thread of tc_wgrad: 0 operand waits, 1 drain waits, 2 total, 3 half-tiles
+__device__ unsigned long long g_dgprof[148][16];   // MMA thread of tc_dgrad: 0 acc_empty, 1 weights, 2 total, 3 tiles, 4 unused, 5..15 a_ready per position
+#define DGP_T0() long long _t0 = clock64()
+#define DGP_ADD(i) do { const long long _t1 = clock64(); _dp[i] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } while (0)
+#define DGP_SKIP() _t0 = clock64()
+#else
+#define DGP_T0()
+#define DGP_ADD(i)
+#define DGP_SKIP()
+#endif
+// dY operand plane of the weight-gradient pass from the [feature/8][128 samples][8] A image in shared memory:
+// plane layout [hi|lo][sample half][feature block][64 samples][8], i.e. every (plane, half, block) is one 1 KB bulk
+// store; thread `i` of the first 2 * nkb threads issues the two stores of (plane i / nkb, block i % nkb).
+__device__ __forceinline__ void store_plane_1k(unsigned char* dst, uint32_t a_hi_s, uint32_t a_lo_s, int i, int nkb) {
+  if (i < 2 * nkb) {
+    const int pl = i / nkb, kb = i - pl * nkb;
+    const uint32_t src = (pl ? a_lo_s : a_hi_s) + kb * 2048;
+    unsigned char* d = dst + (size_t)pl * (nkb * 2048) + kb * 1024;
+    bulk_s2g(d, src, 1024);
+    bulk_s2g(d + nkb * 1024, src + 1024, 1024);
+  }
+  bulk_commit();
+}
+
 template <bool GBF, int CL>
 __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsigned char* __restrict__ wimg, DgradPtrs P, size_t M,
                                                     int n_tiles, int write_dy) {
@@ -175,6 +200,10 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       uint32_t slot = 0, phase = 0;
       const uint32_t a_hi = smem_u32(smem + DG_AHI), a_lo = smem_u32(smem + DG_ALO);
       int tv = 0;
+#ifdef NNB_TC_PROFILE
+      unsigned long long _dp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const long long _tstart = clock64();
+#endif
       for (int tt = 0; tt < my_tiles; ++tt) {
         if (blockIdx.x + tt * gridDim.x >= n_tiles) {   // past the end: keep the shared weight stream flowing
           for (int s = 0; s < N_STAGES_T; ++s) {
@@ -189,8 +218,10 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         for (int pos = 0; pos < N_POS; ++pos) {
           const int buf = pos & 1;
           const uint32_t use = buf ? (uint32_t)t * 5u + (uint32_t)(pos >> 1) : (uint32_t)t * 6u + (uint32_t)(pos >> 1);
+          DGP_T0();
           mbar_wait(BAR(D_ACCEMPTY + buf), (use & 1u) ^ 1u);
           tc_fence_after();
+          DGP_ADD(0);
           const int N = c_pos_N[pos], ksteps = c_pos_ksteps[pos];
           const uint32_t d_tmem = tmem_base + buf * 256;
           const uint32_t idesc = make_idesc_ex(128, N, 1, 1, 0, 0);   // A = gradients, B = transposed weights, both bf16 hi|lo, K-major
@@ -200,11 +231,15 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           uint32_t full_ok = mbar_probe(BAR(D_FULL + slot), phase);   // probe early: the barrier round trip hides under the other waits
           for (int ks = 0; ks < ksteps; ++ks) {
             if ((ks & 3) == 0 && pos != 6) {   // pos 6 re-reads the A version pos 5 already waited for
+              DGP_SKIP();
               mbar_wait(BAR(D_AREADY + (ks >> 2)), aver & 1u);
               tc_fence_after();
+              DGP_ADD(5 + pos);
             }
+            DGP_SKIP();
             if (!full_ok) mbar_wait(BAR(D_FULL + slot), phase);
             tc_fence_after();
+            DGP_ADD(1);
             const uint32_t wb = smem_u32(smem + DG_W + slot * STAGE_BYTES);
             const uint64_t dAh = make_desc(a_hi + ks * 4096, 2048, 128), dAl = make_desc(a_lo + ks * 4096, 2048, 128);
             const uint64_t dBh = make_desc(wb, b_lbo, 128), dBl = make_desc(wb + N * 32, b_lbo, 128);
@@ -222,6 +257,9 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           tc_commit(BAR(D_ACCFULL + buf));
         }
       }
+#ifdef NNB_TC_PROFILE
+      if (blockIdx.x < 148) { _dp[2] = (unsigned long long)(clock64() - _tstart); _dp[3] = tv; for (int i = 0; i < 16; ++i) g_dgprof[blockIdx.x][i] = _dp[i]; }
+#endif
     }
   } else {
     // 8 epilogue warps: two per TMEM lane quarter; `half` selects the column chunks this thread converts
@@ -237,7 +275,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       const int t = ++tv;
       const size_t m = (size_t)tile * TILE + row;
       // ---- prologue: head adjoints -> g_yr (A version 0) ----
-      if (leader) bulk_wait_read0();
+      if (half == 0) bulk_wait_read0();
       epi_bar();
       float g_s;
       {
@@ -267,9 +305,8 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       }
       mbar_arrive(BAR(D_AREADY + 2)); mbar_arrive(BAR(D_AREADY + 3));     // blocks 2,3 are empty in A version 0 (K = 128)
       epi_bar();
-      if (leader && write_dy) {   // dY planes of rgb_layers.0 (128 features = first 32 KB of each image)
-        unsigned char* dst = P.dyp[9] + (size_t)tile * PLANE_TILE_128;
-        bulk_s2g(dst, a_hi_s, 32768); bulk_s2g(dst + 32768, a_lo_s, 32768); bulk_commit();
+      if (half == 0 && write_dy && row < 64) {   // dY planes of rgb_layers.0 (128 features = first 16 blocks of each image)
+        store_plane_1k(P.dyp[9] + (size_t)tile * PLANE_TILE_128, a_hi_s, a_lo_s, row, 16);
       }
       // ---- chain ----
       for (int pos = 0; pos < N_POS; ++pos) {
@@ -278,7 +315,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         mbar_wait(BAR(D_ACCFULL + buf), use & 1u);
         tc_fence_after();
         const bool writes_a = (pos != 5 && pos != 10);
-        if (writes_a) { if (leader) bulk_wait_read0(); epi_bar(); }   // previous image fully read by its bulk store
+        if (writes_a) { if (half == 0) bulk_wait_read0(); epi_bar(); }   // previous image fully read by its bulk stores
         // mask layer: g_y_l = g_h_l * (h_l > 0) with l = 7 (pos1), 6,5,4 (pos2..4), 3 (pos6), 2,1,0 (pos7..9)
         const int mask_l = (pos == 1) ? 7 : (pos >= 2 && pos <= 4) ? 8 - pos : (pos == 6) ? 3 : (pos >= 7 && pos <= 9) ? 9 - pos : -1;
         const uint32_t* mrow = (mask_l >= 0) ? P.mask + ((size_t)mask_l * P.Mpad + m) * 8 : nullptr;
@@ -318,11 +355,10 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         mbar_arrive(BAR(D_ACCEMPTY + buf));
         if (writes_a) {
           epi_bar();
-          if (leader && write_dy) {
+          if (half == 0 && write_dy) {
             // A now holds: pos0 -> g_feat ; pos1 -> g_y7 ; pos2..4 -> g_y6..4 ; pos6 -> g_y3 ; pos7..9 -> g_y2..0
             const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
-            unsigned char* dst = P.dyp[di] + (size_t)tile * PLANE_TILE_256;
-            bulk_s2g(dst, a_hi_s, 65536); bulk_s2g(dst + 65536, a_lo_s, 65536); bulk_commit();
+            store_plane_1k(P.dyp[di] + (size_t)tile * PLANE_TILE_256, a_hi_s, a_lo_s, row, 32);
           }
         }
       }
@@ -335,7 +371,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         P.gp[m] = make_float4(gp[0] * inv_gscale, gp[1] * inv_gscale, gp[2] * inv_gscale, 0.f);
       }
     }
-    if (leader) bulk_wait0();
+    if (half == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -356,154 +392,225 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
 // ---------------------------------------------------------------------------------------------------
 // weight gradients
 // ---------------------------------------------------------------------------------------------------
+// Operand planes (written by tc_field_fwd / tc_dgrad): per 128-sample tile a hi plane then a lo plane, each
+// [sample half h: 2][feature block kb: F/8][64 samples][8 features] bf16, so that one 64-sample half of one
+// plane (or of one 128-feature half of it) is ONE contiguous bulk copy and an MN-major MMA operand as it lands.
 struct WgJob {
   const unsigned char* dy; const unsigned char* x;   // plane bases
-  int dy_tile, dy_plane, dy_off;                     // bytes per tile / per hi plane / offset of this n-half inside a plane
-  int x_tile, x_plane;                               // bytes per tile / per hi plane (65536 or 16384)
-  int N;                                             // 256 | 64
-  int n_base, ldw, kvalid;                           // rows n_base.. of dW, row stride, valid k
-  int w_off, b_off;                                  // float offsets into the flat gradient (b_off < 0: no bias)
+  int dy_tile, dy_feat;                              // bytes per tile (hi + lo), features of the dY plane (256 | 128)
+  int x_tile;                                        // bytes per tile (hi + lo)
+  int N;                                             // 256 | 64: features of the X plane = columns of this dW block
+  int ldw, kvalid, w_off;                            // row stride / valid columns / float offset of dW in the flat gradient
+  int paired;                                        // 1: the two CTAs of a pair take the two 128-row halves of dW; 0: they split the tiles
+  int cost;                                          // bytes-per-tile weight used to balance the CTA pairs
 };
-constexpr int MAX_WG_JOBS = 24;
-struct WgJobs { WgJob j[MAX_WG_JOBS]; int njobs, msplit, n_tiles; };
+constexpr int MAX_WG_JOBS = 12;
+struct WgJobs { WgJob j[MAX_WG_JOBS]; int njobs, n_tiles; };
 
-constexpr int WG_SLOT = 32768, WG_NSLOT = 6;
-constexpr int WG_ONES = WG_NSLOT * WG_SLOT;          // 512 B ones operand
-constexpr int WG_BAR = WG_ONES + 512;
-constexpr int WG_TOTAL = WG_BAR + 16 * 8 + 16;
-enum { G_FULL = 0, G_EMPTY = 6, G_DONE = 12, G_DRAINED = 13 };
+constexpr int WG_SET = 98304;                        // one half-tile operand set: A_hi 16K | A_lo 16K | B_hi 32K | B_lo 32K
+constexpr int WG_AHI = 0, WG_ALO = 16384, WG_BHI = 32768, WG_BLO = 65536;
+constexpr int WG_XPOSE = 2 * WG_SET;                 // 4 warps x [32][17] floats: transposes accumulator rows into coalesced atomics
+constexpr int WG_SEG = WG_XPOSE + 4 * 32 * 17 * 4;   // segment table
+constexpr int WG_BAR = WG_SEG + 16 * 16;
+constexpr int WG_TOTAL = WG_BAR + 20 * 8 + 16;
+enum { G_FULL = 0 /* [set][AHI,ALO,BHI,BLO] */, G_EMPTY = 8, G_DONE = 16, G_DRAINED = 17 };
 // The tensor core adds each K=16 partial product to the fp32 accumulator with truncation, so the error of a long
-// accumulation chain grows linearly (~3e-8 per MMA, measured 2.9e-4 at ~2000 MMAs).  The accumulator is therefore
-// drained to the fp32 gradient buffer every WG_GROUP tiles (24 MMAs each) and restarted from zero.
+// accumulation chain grows linearly (~3e-8 per MMA).  Every WG_GROUP tiles (24 MMAs each) the running accumulator is
+// therefore folded into a second TMEM accumulator with round-to-nearest adds in registers and restarted from zero;
+// only the total of a CTA's segment goes to the flat gradient buffer with atomics.
 constexpr int WG_GROUP = 16;
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+struct WgSeg { int job, t0, t1, pad; };
 
 template <bool GBF>
 __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restrict__ gflat, const unsigned int* __restrict__ gmax) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const WgJob J = jobs.j[blockIdx.x / jobs.msplit];
-  const int split = blockIdx.x % jobs.msplit;
-  const int per = (jobs.n_tiles + jobs.msplit - 1) / jobs.msplit;
-  const int t0 = split * per, t1 = min(jobs.n_tiles, t0 + per);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + WG_BAR + 16 * 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + WG_BAR + 20 * 8);
+  WgSeg* segs = reinterpret_cast<WgSeg*>(smem + WG_SEG);
+  __shared__ int s_nseg;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int side = blockIdx.x & 1;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WG_NSLOT; ++i) { mbar_init(BAR(G_FULL + i), 1); mbar_init(BAR(G_EMPTY + i), 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(BAR(G_FULL + i), 1); mbar_init(BAR(G_EMPTY + i), 1); }
     mbar_init(BAR(G_DONE), 1); mbar_init(BAR(G_DRAINED), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // this CTA pair's share of the work: an equal slice of the cost line  sum_j cost_j * n_tiles, cut at tile boundaries
+    const long long P = gridDim.x >> 1, p = blockIdx.x >> 1;
+    long long U = 0;
+    for (int j = 0; j < jobs.njobs; ++j) U += (long long)jobs.j[j].cost * jobs.n_tiles;
+    const long long lo = U * p / P, hi = U * (p + 1) / P;
+    long long u0 = 0;
+    int ns = 0;
+    for (int j = 0; j < jobs.njobs; ++j) {
+      const long long c = jobs.j[j].cost, u1 = u0 + c * jobs.n_tiles;
+      const long long a = lo > u0 ? lo : u0, b = hi < u1 ? hi : u1;
+      if (b > a) {
+        int t0 = (int)((a - u0 + c - 1) / c), t1 = (int)((b - u0 + c - 1) / c);
+        if (!jobs.j[j].paired) { const int mid = (t0 + t1) >> 1; if (side == 0) t1 = mid; else t0 = mid; }
+        if (t1 > t0 && ns < 16) { segs[ns].job = j; segs[ns].t0 = t0; segs[ns].t1 = t1; ++ns; }
+      }
+      u0 = u1;
+    }
+    s_nseg = ns;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x < 128) {   // ones operand: [2 n'-blocks][16 samples][8] fp16, (m, n'=0) = 1
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(smem + WG_ONES);
-    for (int i = threadIdx.x; i < 256; i += 128) o[i] = __float2bfloat16((i < 128 && (i & 7) == 0) ? 1.f : 0.f);
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool big = (J.N == 256);
-  const int xbytes = big ? 32768 : 16384;
+  const int nseg = s_nseg;
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t phase = 0;
-      for (int t = t0; t < t1; ++t) {
-        const unsigned char* dyt = J.dy + (size_t)t * J.dy_tile + J.dy_off;
-        const unsigned char* xt = J.x + (size_t)t * J.x_tile;
-        const unsigned char* src[6] = {dyt, xt, xt + 32768, xt + J.x_plane, xt + J.x_plane + 32768, dyt + J.dy_plane};
-        const int nb[6] = {32768, xbytes, big ? 32768 : 0, xbytes, big ? 32768 : 0, 32768};
+      uint32_t it = 0;   // half-tile counter: operand set = it & 1, barrier phase = (it >> 1) & 1
+      for (int si = 0; si < nseg; ++si) {
+        const WgSeg sg = segs[si];
+        const WgJob& J = jobs.j[sg.job];
+        const int dy_plane = J.dy_tile >> 1, dy_half = dy_plane >> 1, x_plane = J.x_tile >> 1, x_half = x_plane >> 1;
+        const int dy_off = (J.paired && J.dy_feat == 256) ? side * 16384 : 0;
+        for (int t = sg.t0; t < sg.t1; ++t) {
+          const unsigned char* dyt = J.dy + (size_t)t * J.dy_tile + dy_off;
+          const unsigned char* xt = J.x + (size_t)t * J.x_tile;
 #pragma unroll
-        for (int s = 0; s < 6; ++s) {
-          if (nb[s] == 0) continue;
-          mbar_wait(BAR(G_EMPTY + s), phase ^ 1);
-          mbar_expect_tx(BAR(G_FULL + s), nb[s]);
-          bulk_g2s(smem_u32(smem + s * WG_SLOT), src[s], nb[s], BAR(G_FULL + s));
+          for (int h = 0; h < 2; ++h, ++it) {
+            const int set = it & 1;
+            const uint32_t ph = ((it >> 1) & 1u) ^ 1u, sb = smem_u32(smem + set * WG_SET);
+            const unsigned char* src[4] = {dyt + h * dy_half, xt + h * x_half, xt + x_plane + h * x_half, dyt + dy_plane + h * dy_half};
+            const int dsto[4] = {WG_AHI, WG_BHI, WG_BLO, WG_ALO}, bi[4] = {0, 2, 3, 1};
+            const int nb[4] = {16384, x_half, x_half, 16384};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              mbar_wait(BAR(G_EMPTY + set * 4 + bi[c]), ph);
+              mbar_expect_tx(BAR(G_FULL + set * 4 + bi[c]), nb[c]);
+              bulk_g2s(sb + dsto[c], src[c], nb[c], BAR(G_FULL + set * 4 + bi[c]));
+            }
+          }
         }
-        phase ^= 1;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t phase = 0;
-      // A = dY planes, B = activation planes / ones: all bf16 hi|lo, MN-major (tcgen05 kind::f16 needs one format for A and B)
-      const uint32_t idesc = make_idesc_ex(128, J.N, 1, 1, 1, 1), idesc1 = make_idesc_ex(128, 16, 1, 1, 1, 1);
-      const uint32_t s0 = smem_u32(smem), ones = smem_u32(smem + WG_ONES);
-      const uint32_t d_main = tmem_base, d_bias = tmem_base + 256;
-      const uint32_t xsbo = big ? 2048u : 2048u;
-      uint32_t first = 0, gphase = 0, okm = 0;
-      for (int t = t0; t < t1; ++t) {
-        // products: (A_hi,B_hi) (A_hi,B_lo) (A_lo,B_hi); A = slot0 / slot5, B_hi = slot1(+2), B_lo = slot3(+4)
-        {   // probe all barriers of this tile back to back (their ~110-cycle round trips overlap), block only on the late ones
-          uint32_t ok[6];
+      // A = dY planes (M = 128 features of this CTA's half, K = samples), B = activation planes (N features, K = samples):
+      // bf16 hi|lo, MN-major.  Products per K-step: (A_hi,B_hi) (A_hi,B_lo) (A_lo,B_hi).
+      uint32_t it = 0, gcount = 0;
+#ifdef NNB_TC_PROFILE
+      unsigned long long _dp[4] = {0, 0, 0, 0};
+      const long long _tstart = clock64();
+#endif
+      for (int si = 0; si < nseg; ++si) {
+        const WgSeg sg = segs[si];
+        const WgJob& J = jobs.j[sg.job];
+        const uint32_t idesc = make_idesc_ex(128, J.N, 1, 1, 1, 1);
+        uint32_t acc = 0;
+        for (int t = sg.t0; t < sg.t1; ++t) {
+          DGP_T0();
+          if (acc == 0 && gcount > 0) { mbar_wait(BAR(G_DRAINED), (gcount - 1) & 1u); tc_fence_after(); }
+          DGP_ADD(1);
 #pragma unroll
-          for (int i = 0; i < 6; ++i) ok[i] = mbar_probe(BAR(G_FULL + i), phase);
-          if (!ok[0]) mbar_wait(BAR(G_FULL + 0), phase);
-          if (!ok[1]) mbar_wait(BAR(G_FULL + 1), phase);
-          if (big && !ok[2]) mbar_wait(BAR(G_FULL + 2), phase);
-          okm = ok[3] | (ok[4] << 1) | (ok[5] << 2);
-        }
-        tc_fence_after();
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t dA = make_desc(s0 + ks * 256, 128, 2048), dB = make_desc(s0 + WG_SLOT + ks * 256, 128, xsbo);
-          tc_mma_f16(d_main, dA, dB, idesc, first | (uint32_t)(ks > 0));
-          if (J.b_off >= 0) tc_mma_f16(d_bias, dA, make_desc(ones, 128, 256), idesc1, first | (uint32_t)(ks > 0));
-        }
-        first = 1u;
-        if (!(okm & 1u)) mbar_wait(BAR(G_FULL + 3), phase);
-        if (big && !(okm & 2u)) mbar_wait(BAR(G_FULL + 4), phase);
-        tc_fence_after();
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t dA = make_desc(s0 + ks * 256, 128, 2048), dB = make_desc(s0 + 3 * WG_SLOT + ks * 256, 128, xsbo);
-          tc_mma_f16(d_main, dA, dB, idesc, 1u);
-        }
-        tc_commit(BAR(G_EMPTY + 0)); tc_commit(BAR(G_EMPTY + 3)); if (big) tc_commit(BAR(G_EMPTY + 4));
-        if (!(okm & 4u)) mbar_wait(BAR(G_FULL + 5), phase);
-        tc_fence_after();
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t dA = make_desc(s0 + 5 * WG_SLOT + ks * 256, 128, 2048), dB = make_desc(s0 + WG_SLOT + ks * 256, 128, xsbo);
-          tc_mma_f16(d_main, dA, dB, idesc, 1u);
-          if (J.b_off >= 0) tc_mma_f16(d_bias, dA, make_desc(ones, 128, 256), idesc1, 1u);
-        }
-        tc_commit(BAR(G_EMPTY + 1)); if (big) tc_commit(BAR(G_EMPTY + 2)); tc_commit(BAR(G_EMPTY + 5));
-        phase ^= 1;
-        if (((t - t0 + 1) % WG_GROUP) == 0 || t + 1 == t1) {   // hand the accumulator to the epilogue warps, restart from zero
-          tc_commit(BAR(G_DONE));
-          if (t + 1 < t1) { mbar_wait(BAR(G_DRAINED), gphase); tc_fence_after(); gphase ^= 1; first = 0; }
+          for (int h = 0; h < 2; ++h, ++it) {
+            const int set = it & 1;
+            const uint32_t ph = (it >> 1) & 1u, sb = smem_u32(smem + set * WG_SET);
+            uint32_t ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ok[i] = mbar_probe(BAR(G_FULL + set * 4 + i), ph);   // round trips overlap
+            DGP_SKIP();
+            if (!ok[0]) mbar_wait(BAR(G_FULL + set * 4 + 0), ph);
+            if (!ok[2]) mbar_wait(BAR(G_FULL + set * 4 + 2), ph);
+            tc_fence_after();
+            DGP_ADD(0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc_mma_f16(tmem_base, make_desc(sb + WG_AHI + ks * 256, 128, 1024), make_desc(sb + WG_BHI + ks * 256, 128, 1024), idesc, acc | (uint32_t)(ks > 0));
+            }
+            acc = 1u;
+            DGP_SKIP();
+            if (!ok[3]) mbar_wait(BAR(G_FULL + set * 4 + 3), ph);
+            tc_fence_after();
+            DGP_ADD(0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_f16(tmem_base, make_desc(sb + WG_AHI + ks * 256, 128, 1024), make_desc(sb + WG_BLO + ks * 256, 128, 1024), idesc, 1u);
+            tc_commit(BAR(G_EMPTY + set * 4 + 0)); tc_commit(BAR(G_EMPTY + set * 4 + 3));
+            DGP_SKIP();
+            if (!ok[1]) mbar_wait(BAR(G_FULL + set * 4 + 1), ph);
+            tc_fence_after();
+            DGP_ADD(0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_f16(tmem_base, make_desc(sb + WG_ALO + ks * 256, 128, 1024), make_desc(sb + WG_BHI + ks * 256, 128, 1024), idesc, 1u);
+            tc_commit(BAR(G_EMPTY + set * 4 + 1)); tc_commit(BAR(G_EMPTY + set * 4 + 2));
+          }
+          if (((t - sg.t0 + 1) % WG_GROUP) == 0 || t + 1 == sg.t1) { tc_commit(BAR(G_DONE)); ++gcount; acc = 0; }
         }
       }
+#ifdef NNB_TC_PROFILE
+      if (blockIdx.x < 148) { _dp[2] = (unsigned long long)(clock64() - _tstart); _dp[3] = it; for (int i = 0; i < 4; ++i) g_wgprof[blockIdx.x][i] = _dp[i]; }
+#endif
     }
   } else {
-    const int q = warp & 3, row = q * 32 + lane;
-    const int ngroups = (t1 - t0 + WG_GROUP - 1) / WG_GROUP;
-    for (int gi = 0; gi < ngroups; ++gi) {
-      mbar_wait(BAR(G_DONE), (uint32_t)gi & 1u);
-      tc_fence_after();
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const float inv_gscale = GBF ? 1.f : 1.f / grad_scale_from(gmax);     // fp16 dY planes carry the chain's power-of-two scale
-      float* dst = gflat + J.w_off + (size_t)(J.n_base + row) * J.ldw;
-      const int nchunks = J.N / 32;
-      for (int cb = 0; cb < nchunks; ++cb) {
-        uint32_t r[32];
-        tc_ld32(lane_addr + cb * 32, r);
+    const int q = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* xp = reinterpret_cast<float*>(smem + WG_XPOSE) + q * (32 * 17);
+    uint32_t gcount = 0;
+    for (int si = 0; si < nseg; ++si) {
+      const WgSeg sg = segs[si];
+      const WgJob& J = jobs.j[sg.job];
+      const int n_base = (J.paired && J.dy_feat == 256) ? side * 128 : 0;
+      float* dst0 = gflat + J.w_off + (size_t)(n_base + q * 32) * J.ldw;
+      const int ngroups = (sg.t1 - sg.t0 + WG_GROUP - 1) / WG_GROUP, nchunks = J.N / 32;
+      for (int gi = 0; gi < ngroups; ++gi, ++gcount) {
+        mbar_wait(BAR(G_DONE), gcount & 1u);
+        tc_fence_after();
+        const bool last = (gi + 1 == ngroups);
+        for (int cb = 0; cb < nchunks; ++cb) {
+          uint32_t r[32];
+          tc_ld32(lane_addr + cb * 32, r);
+          if (gi > 0) {
+            uint32_t r2[32];
+            tc_ld32(lane_addr + 256 + cb * 32, r2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = cb * 32 + j;
-          if (k < J.kvalid) atomicAdd(dst + k, __uint_as_float(r[j]) * inv_gscale);
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
+          if (!last) {
+            tc_st32(lane_addr + 256 + cb * 32, r);
+          } else {   // segment total -> flat gradient: rows of this warp's 32 x 32 block become 64-byte runs of atomics
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xp[lane * 17 + j] = __uint_as_float(r[hc * 16 + j]);
+              __syncwarp();
+              const int k = cb * 32 + hc * 16 + (lane & 15);
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) {
+                const int rw = rr + (lane >> 4);
+                if (k < J.kvalid) atomicAdd(dst0 + (size_t)rw * J.ldw + k, xp[rw * 17 + (lane & 15)]);
+              }
+              __syncwarp();
+            }
+          }
         }
+        if (!last) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(BAR(G_DRAINED));
       }
-      if (J.b_off >= 0) {
-        uint32_t r[32];
-        tc_ld32(lane_addr + 256, r);
-        atomicAdd(gflat + J.b_off + J.n_base + row, __uint_as_float(r[0]) * inv_gscale);
-      }
-      tc_fence_before();
-      mbar_arrive(BAR(G_DRAINED));
     }
   }
   tc_fence_before();
@@ -621,6 +728,15 @@ cudaError_t upload_stage_table_t() {
 
 }  // namespace
 
+#ifdef NNB_TC_PROFILE
+extern "C" int nnb_debug_wgprof(unsigned long long* host148x8) {
+  return (int)cudaMemcpyFromSymbol(host148x8, g_wgprof, sizeof(unsigned long long) * 148 * 8);
+}
+extern "C" int nnb_debug_dgprof(unsigned long long* host148x16) {
+  return (int)cudaMemcpyFromSymbol(host148x16, g_dgprof, sizeof(unsigned long long) * 148 * 16);
+}
+#endif
+
 size_t tc_bwd_workspace_extra() { return align_up(IMG_T_BYTES, 256); }
 
 cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L, size_t img_t_offset, cudaStream_t st) {
@@ -672,43 +788,64 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   else e = launch_clustered(tc_dgrad<true, 1>, grid_d, 320, DG_TOTAL, 1, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
+  // fork: the streaming head / direction reductions (fp32 side stashes) run beside tc_wgrad on a second stream
+  static cudaStream_t aux = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static const bool use_aux = [] { const char* v = getenv("NNB_AUX_STREAM"); return !(v && v[0] == '0'); }();
+  if (use_aux && !aux) {
+    e = cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaStream_t sx = use_aux ? aux : st;
+  if (use_aux) {
+    e = cudaEventRecord(ev_fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(aux, ev_fork, 0);
+    if (e != cudaSuccess) return e;
+  }
   if (b.g_weights) {
     WgJobs J{};
     int nj = 0;
-    auto add = [&](int dyi, int dy_feat, int half, int xi, int N, int w_off, int ldw, int kvalid, int b_off) {
+    auto add = [&](int dyi, int dy_feat, int xi, int N, int w_off, int ldw, int kvalid, int paired, int cost) {
       WgJob& j = J.j[nj++];
       j.dy = reinterpret_cast<const unsigned char*>(base + L.dyp[dyi]);
-      j.dy_tile = dy_feat == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_128; j.dy_plane = j.dy_tile / 2; j.dy_off = half * 32768;
+      j.dy_tile = dy_feat == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_128; j.dy_feat = dy_feat;
       j.x = reinterpret_cast<const unsigned char*>(base + L.xp[xi]);
-      j.x_tile = N == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_64; j.x_plane = j.x_tile / 2;
-      j.N = N; j.n_base = half * 128; j.ldw = ldw; j.kvalid = kvalid; j.w_off = w_off; j.b_off = b_off;
+      j.x_tile = N == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_64;
+      j.N = N; j.ldw = ldw; j.kvalid = kvalid; j.w_off = w_off; j.paired = paired; j.cost = cost;
     };
-    for (int half = 0; half < 2; ++half) {
-      add(0, 256, half, 0, 64, nnb::w_off(0), 63, 63, -1);                                 // layer 0: X = enc (biases: tc_dgrad)
-      for (int l = 1; l < 8; ++l) add(l, 256, half, l, 256, nnb::w_off(l), nnb::w_ld(l), 256, -1);   // X = h[l-1] = xp[l]
-      add(4, 256, half, 0, 64, nnb::w_off(4) + 256, 319, 63, -1);                          // layer 4 enc slice
-      add(8, 256, half, 8, 256, nnb::W_FEAT, 256, 256, -1);                                // fc_feature: X = h7 = xp[8]
-    }
-    add(9, 128, 0, 9, 256, nnb::W_RGBH, 283, 256, -1);                                     // rgb_layers.0[:, :256]: X = feat (bias: ray_dir_grad)
+    // cost = bytes one CTA of the pair streams per tile, in units of 96 KB (biases: tc_dgrad / ray_dir_grad)
+    add(0, 256, 0, 64, nnb::w_off(0), 63, 63, 1, 1);                                        // layer 0: X = enc
+    for (int l = 1; l < 8; ++l) add(l, 256, l, 256, nnb::w_off(l), nnb::w_ld(l), 256, 1, 2);   // X = h[l-1] = xp[l]
+    add(4, 256, 0, 64, nnb::w_off(4) + 256, 319, 63, 1, 1);                                 // layer 4 enc slice
+    add(8, 256, 8, 256, nnb::W_FEAT, 256, 256, 1, 2);                                       // fc_feature: X = h7 = xp[8]
+    add(9, 128, 9, 256, nnb::W_RGBH, 283, 256, 0, 1);                                       // rgb_layers.0[:, :256]: X = feat; the pair splits the tiles
     J.njobs = nj; J.n_tiles = n_tiles;
-    int msplit = n_sm / nj; if (msplit < 1) msplit = 1; if (msplit > n_tiles) msplit = n_tiles;
-    J.msplit = msplit;
-    tc_wgrad<true><<<nj * msplit, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);
+    const int grid_w = n_sm >= 2 ? (n_sm / 2) * 2 : 2;
+    tc_wgrad<true><<<grid_w, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     {  // small heads: fc_density / fc_rgb (streaming reduction); the direction slice of rgb_layers.0 rides on ray_dir_grad
       const int chunk = 256;
-      head_wgrad<<<(unsigned)((L.M + chunk - 1) / chunk), 256, 0, st>>>(reinterpret_cast<const float4*>(base + L.dyc),
+      head_wgrad<<<(unsigned)((L.M + chunk - 1) / chunk), 256, 0, sx>>>(reinterpret_cast<const float4*>(base + L.dyc),
                                                                          reinterpret_cast<const float*>(base + L.h[7]),
                                                                          reinterpret_cast<const float*>(base + L.hr), L.M, chunk, b.g_weights);
       e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
   }
-  nnb_prof_mark(st);
-  ray_dir_grad<<<(a.N + 7) / 8, 256, 0, st>>>(a, reinterpret_cast<const float*>(base + L.dyr), reinterpret_cast<const float*>(base + L.denc), gv,
+  ray_dir_grad<<<(a.N + 7) / 8, 256, 0, sx>>>(a, reinterpret_cast<const float*>(base + L.dyr), reinterpret_cast<const float*>(base + L.denc), gv,
                                               b.g_weights ? b.g_weights + nnb::W_RGBH + 256 : nullptr,
                                               b.g_weights ? b.g_weights + nnb::B_RGBH : nullptr);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (use_aux) {
+    e = cudaEventRecord(ev_join, aux);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev_join, 0);
+    if (e != cudaSuccess) return e;
+  }
+  nnb_prof_mark(st);
   e = launch_ray_bwd(b, recs, gp, gv, st);
   nnb_prof_mark(st);
   return e;
