@@ -126,20 +126,6 @@ __device__ unsigned long long g_dgprof[148][16];   // MMA thread of tc_dgrad: 0 
 #define DGP_ADD(i)
 #define DGP_SKIP()
 #endif
-// dY operand plane of the weight-gradient pass from the [feature/8][128 samples][8] A image in shared memory:
-// plane layout [hi|lo][sample half][feature block][64 samples][8], i.e. every (plane, half, block) is one 1 KB bulk
-// store; thread `i` of the first 2 * nkb threads issues the two stores of (plane i / nkb, block i % nkb).
-__device__ __forceinline__ void store_plane_1k(unsigned char* dst, uint32_t a_hi_s, uint32_t a_lo_s, int i, int nkb) {
-  if (i < 2 * nkb) {
-    const int pl = i / nkb, kb = i - pl * nkb;
-    const uint32_t src = (pl ? a_lo_s : a_hi_s) + kb * 2048;
-    unsigned char* d = dst + (size_t)pl * (nkb * 2048) + kb * 1024;
-    bulk_s2g(d, src, 1024);
-    bulk_s2g(d + nkb * 1024, src + 1024, 1024);
-  }
-  bulk_commit();
-}
-
 template <bool GBF, int CL>
 __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsigned char* __restrict__ wimg, DgradPtrs P, size_t M,
                                                     int n_tiles, int write_dy) {
@@ -264,7 +250,6 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   } else {
     // 8 epilogue warps: two per TMEM lane quarter; `half` selects the column chunks this thread converts
     const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;
-    const bool leader = (row == 0 && half == 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     unsigned char* A_hi = smem + DG_AHI; unsigned char* A_lo = smem + DG_ALO;
     const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo);
@@ -275,7 +260,6 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       const int t = ++tv;
       const size_t m = (size_t)tile * TILE + row;
       // ---- prologue: head adjoints -> g_yr (A version 0) ----
-      if (half == 0) bulk_wait_read0();
       epi_bar();
       float g_s;
       {
@@ -287,6 +271,9 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         gyc0 *= gscale; gyc1 *= gscale; gyc2 *= gscale; g_s *= gscale;
         const float* hr = P.hr + m * 128;
         float* dyr = P.dyr + m * 128;
+        // dY operand planes of the weight-gradient pass ([hi|lo][sample half][feature block][64 samples][8] bf16) are
+        // streamed from registers next to the shared-memory image (the bulk-copy engine stays free for the weight ring)
+        unsigned char* gpl = write_dy ? P.dyp[9] + (size_t)tile * PLANE_TILE_128 + (row >> 6) * 16384 + (row & 63) * 16 : nullptr;
 #pragma unroll 1
         for (int ji = 0; ji < 8; ++ji) {
           const int jb = 2 * ji + half;       // halves interleave 8-column groups: 64-column block b is done after ji = 4b+3
@@ -297,17 +284,13 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
             float x = gyc0 * s_small[jb * 8 + j] + gyc1 * s_small[128 + jb * 8 + j] + gyc2 * s_small[256 + jb * 8 + j];
             v[j] = hv[j] > 0.f ? x : 0.f;
           }
-          split_g(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16);
+          split_store8_bf16_dual(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16, gpl ? gpl + jb * 1024 : nullptr, gpl + 32768 + jb * 1024);
           *reinterpret_cast<float4*>(dyr + jb * 8) = make_float4(v[0] * inv_gscale, v[1] * inv_gscale, v[2] * inv_gscale, v[3] * inv_gscale);
           *reinterpret_cast<float4*>(dyr + jb * 8 + 4) = make_float4(v[4] * inv_gscale, v[5] * inv_gscale, v[6] * inv_gscale, v[7] * inv_gscale);
           if ((ji & 3) == 3) { fence_async_smem(); mbar_arrive(BAR(D_AREADY + (ji >> 2))); }   // block 0 / 1 of g_yr complete (256 arrivals)
         }
       }
       mbar_arrive(BAR(D_AREADY + 2)); mbar_arrive(BAR(D_AREADY + 3));     // blocks 2,3 are empty in A version 0 (K = 128)
-      epi_bar();
-      if (half == 0 && write_dy && row < 64) {   // dY planes of rgb_layers.0 (128 features = first 16 blocks of each image)
-        store_plane_1k(P.dyp[9] + (size_t)tile * PLANE_TILE_128, a_hi_s, a_lo_s, row, 16);
-      }
       // ---- chain ----
       for (int pos = 0; pos < N_POS; ++pos) {
         const int buf = pos & 1;
@@ -315,11 +298,13 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         mbar_wait(BAR(D_ACCFULL + buf), use & 1u);
         tc_fence_after();
         const bool writes_a = (pos != 5 && pos != 10);
-        if (writes_a) { if (half == 0) bulk_wait_read0(); epi_bar(); }   // previous image fully read by its bulk stores
         // mask layer: g_y_l = g_h_l * (h_l > 0) with l = 7 (pos1), 6,5,4 (pos2..4), 3 (pos6), 2,1,0 (pos7..9)
         const int mask_l = (pos == 1) ? 7 : (pos >= 2 && pos <= 4) ? 8 - pos : (pos == 6) ? 3 : (pos >= 7 && pos <= 9) ? 9 - pos : -1;
         const uint32_t* mrow = (mask_l >= 0) ? P.mask + ((size_t)mask_l * P.Mpad + m) * 8 : nullptr;
         const int nch = (pos == 5 || pos == 10) ? 1 : 4;   // 32-column chunks handled by this half
+        // A will hold: pos0 -> g_feat ; pos1 -> g_y7 ; pos2..4 -> g_y6..4 ; pos6 -> g_y3 ; pos7..9 -> g_y2..0
+        const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
+        unsigned char* gpl = (write_dy && writes_a) ? P.dyp[di] + (size_t)tile * PLANE_TILE_256 + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
 #pragma unroll 1
         for (int ci = 0; ci < nch; ++ci) {
           const int cb = (nch == 1) ? half : 2 * ci + half;    // halves share each 64-column block (ready after one chunk time)
@@ -342,10 +327,10 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           } else {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
-              split_g(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16);
+              split_store8_bf16_dual(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16,
+                                     gpl ? gpl + (cb * 4 + kb) * 1024 : nullptr, gpl + 65536 + (cb * 4 + kb) * 1024);
             fence_async_smem(); mbar_arrive(BAR(D_AREADY + ci));
             if (write_dy) {   // bias gradient of this layer: db[n] = sum_m dY[m][n] (off the MMA's critical path)
-              const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
               const float cs = warp_colsum32(v, lane);
               atomicAdd(&s_colsum[di * 256 + cb * 32 + lane], cs * inv_gscale);
             }
@@ -353,14 +338,6 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         }
         tc_fence_before();
         mbar_arrive(BAR(D_ACCEMPTY + buf));
-        if (writes_a) {
-          epi_bar();
-          if (half == 0 && write_dy) {
-            // A now holds: pos0 -> g_feat ; pos1 -> g_y7 ; pos2..4 -> g_y6..4 ; pos6 -> g_y3 ; pos7..9 -> g_y2..0
-            const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
-            store_plane_1k(P.dyp[di] + (size_t)tile * PLANE_TILE_256, a_hi_s, a_lo_s, row, 32);
-          }
-        }
       }
       // ---- encoding adjoint (both halves' columns of g_enc are in shared memory) ----
       epi_bar();
@@ -371,7 +348,6 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         P.gp[m] = make_float4(gp[0] * inv_gscale, gp[1] * inv_gscale, gp[2] * inv_gscale, 0.f);
       }
     }
-    if (half == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -815,12 +791,12 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
       j.x_tile = N == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_64;
       j.N = N; j.ldw = ldw; j.kvalid = kvalid; j.w_off = w_off; j.paired = paired; j.cost = cost;
     };
-    // cost = bytes one CTA of the pair streams per tile, in units of 96 KB (biases: tc_dgrad / ray_dir_grad)
-    add(0, 256, 0, 64, nnb::w_off(0), 63, 63, 1, 1);                                        // layer 0: X = enc
-    for (int l = 1; l < 8; ++l) add(l, 256, l, 256, nnb::w_off(l), nnb::w_ld(l), 256, 1, 2);   // X = h[l-1] = xp[l]
-    add(4, 256, 0, 64, nnb::w_off(4) + 256, 319, 63, 1, 1);                                 // layer 4 enc slice
-    add(8, 256, 8, 256, nnb::W_FEAT, 256, 256, 1, 2);                                       // fc_feature: X = h7 = xp[8]
-    add(9, 128, 9, 256, nnb::W_RGBH, 283, 256, 0, 1);                                       // rgb_layers.0[:, :256]: X = feat; the pair splits the tiles
+    // cost = measured MMA-thread cycles per tile and CTA pair (N = 256 tiles are DRAM-bound, N = 64 tiles issue-bound), /80
+    add(0, 256, 0, 64, nnb::w_off(0), 63, 63, 1, 40);                                        // layer 0: X = enc (biases: tc_dgrad / ray_dir_grad)
+    for (int l = 1; l < 8; ++l) add(l, 256, l, 256, nnb::w_off(l), nnb::w_ld(l), 256, 1, 54);   // X = h[l-1] = xp[l]
+    add(4, 256, 0, 64, nnb::w_off(4) + 256, 319, 63, 1, 40);                                 // layer 4 enc slice
+    add(8, 256, 8, 256, nnb::W_FEAT, 256, 256, 1, 54);                                       // fc_feature: X = h7 = xp[8]
+    add(9, 128, 9, 256, nnb::W_RGBH, 283, 256, 0, 27);                                       // rgb_layers.0[:, :256]: X = feat; the pair splits the tiles
     J.njobs = nj; J.n_tiles = n_tiles;
     const int grid_w = n_sm >= 2 ? (n_sm / 2) * 2 : 2;
     tc_wgrad<true><<<grid_w, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);

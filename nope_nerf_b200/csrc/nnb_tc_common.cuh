@@ -128,6 +128,23 @@ __device__ __forceinline__ void split_stream8_bf16(const float* v, unsigned char
   st_stream16(hi_dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
   st_stream16(lo_dst, make_uint4(lo[0], lo[1], lo[2], lo[3]));
 }
+// bf16 hi/lo split stored twice: shared-memory operand image (next MMA) + streaming global copy (operand plane)
+__device__ __forceinline__ void split_store8_bf16_dual(const float* v, unsigned char* hi_s, unsigned char* lo_s, unsigned char* hi_g, unsigned char* lo_g) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<uint32_t*>(&hh);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+    hi[i] = hb;
+    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]), L = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<uint4*>(hi_s) = H;
+  *reinterpret_cast<uint4*>(lo_s) = L;
+  if (hi_g) { st_stream16(hi_g, H); st_stream16(lo_g, L); }
+}
 // instruction descriptor with explicit operand formats (0 = fp16, 1 = bf16) and major-ness (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t make_idesc_ex(int M, int N, int afmt, int bfmt, int amaj, int bmaj) {
   return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)amaj << 15) | ((uint32_t)bmaj << 16) |
