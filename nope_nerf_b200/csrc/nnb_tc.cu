@@ -347,22 +347,57 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         const bool planes = stash && (st.tcb & 1);
         const int dbg = st.tcb >> 1;
         unsigned char* xplane = (planes && g < 9 && !(dbg & 1)) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
-        // pass 1 (critical path of the MMA warp): accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand, block by block.
-        // The two halves convert adjacent 32-column chunks of the SAME 64-column block, so block `ci` is complete
-        // after one chunk time.
-        if (g < 9) {
-#pragma unroll 1
-          for (int ci = 0; ci < nch; ++ci) {
-            const int cb = 2 * ci + half;
-            uint32_t r[32];
-            tc_ld32(lane_addr + buf * 256 + cb * 32, r);
-            PROF_ADD(2);
-            float v[32];
+        // Per 32-column chunk: (1) critical path of the MMA warp: accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand,
+        // block by block (the two halves convert adjacent chunks of the SAME 64-column block, so block `ci` is complete
+        // after one chunk time); (2) after the block is signalled, from the same registers, everything the next MMA does
+        // not need: density / colour heads, fp32 side stash, bf16 operand planes, ReLU bitmasks.  One chunk takes less
+        // than the 4 K-steps (~1.5k cycles) the tensor core spends on a block, so (2) never starves the MMA warp.
+        const bool two_pass = (dbg & 8) != 0;    // experiment knob: re-read the accumulator in a second pass (round-1 layout)
+        const bool need2 = (g == 7) || (g == 9) || stash;
+        auto side_work = [&](int cb, const float* v) {
+          if (g == 7) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s_logit = fmaf(v[j], s_bias[2304 + cb * 32 + j], s_logit);
+          }
+          if (g == 9) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
-              v[j] = (g == 8) ? x : fmaxf(x, 0.f);
+              c_acc[0] = fmaf(v[j], s_bias[2560 + cb * 32 + j], c_acc[0]);
+              c_acc[1] = fmaf(v[j], s_bias[2560 + 128 + cb * 32 + j], c_acc[1]);
+              c_acc[2] = fmaf(v[j], s_bias[2560 + 256 + cb * 32 + j], c_acc[2]);
             }
+          }
+          if (stash && (!planes || g == 7 || g == 9)) {
+            float* dst = (g < 8) ? st.h[g] + m * 256 : (g == 8 ? st.feat + m * 256 : st.hr + m * 128);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              __stcs(reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4), make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+          }
+          if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi|lo, coalesced 512 B per warp
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+              split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024);
+          }
+          if (planes && (g < 8 || g == 9) && !(dbg & 2)) {   // ReLU bitmask of this 32-column chunk (g = 9: rgb hidden layer, slot 8)
+            uint32_t mw = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
+            __stcs(st.mask + ((size_t)(g < 8 ? g : 8) * st.Mpad + m) * 8 + cb, mw);
+          }
+        };
+#pragma unroll 1
+        for (int ci = 0; ci < nch; ++ci) {
+          const int cb = 2 * ci + half;
+          uint32_t r[32];
+          tc_ld32(lane_addr + buf * 256 + cb * 32, r);
+          PROF_ADD(2);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
+            v[j] = (g == 8) ? x : fmaxf(x, 0.f);
+          }
+          if (g < 9) {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
               const int kblock = cb * 4 + kb;
@@ -374,11 +409,9 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             mbar_arrive(BAR(B_AREADY + ci));     // 256 arrivals (both halves) complete block ci
             PROF_ADD(5);
           }
+          if (need2 && !two_pass) side_work(cb, v);
         }
-        // pass 2 (overlaps the next layer's MMAs): re-read the accumulator for everything that is NOT needed by the
-        // next MMA: density / colour heads, fp32 side stash, bf16 operand planes, ReLU bitmasks
-        const bool need2 = (g == 7) || (g == 9) || stash;
-        if (need2) {
+        if (need2 && two_pass) {
 #pragma unroll 1
           for (int ci = 0; ci < nch; ++ci) {
             const int cb = 2 * ci + half;
@@ -390,41 +423,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
               float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
               v[j] = (g == 8) ? x : fmaxf(x, 0.f);
             }
-            if (g == 7) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) s_logit = fmaf(v[j], s_bias[2304 + cb * 32 + j], s_logit);
-            }
-            if (g == 9) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                c_acc[0] = fmaf(v[j], s_bias[2560 + cb * 32 + j], c_acc[0]);
-                c_acc[1] = fmaf(v[j], s_bias[2560 + 128 + cb * 32 + j], c_acc[1]);
-                c_acc[2] = fmaf(v[j], s_bias[2560 + 256 + cb * 32 + j], c_acc[2]);
-              }
-            }
-            if (stash && (!planes || g == 7 || g == 9)) {
-              float* dst = (g < 8) ? st.h[g] + m * 256 : (g == 8 ? st.feat + m * 256 : st.hr + m * 128);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4)
-                __stcs(reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4), make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-            }
-            if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi|lo, coalesced 512 B per warp
-              if (dbg & 4) {
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb)
-                  split_store8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024);
-              } else {
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb)
-                  split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024);
-              }
-            }
-            if (planes && g < 8 && !(dbg & 2)) {   // ReLU bitmask of this 32-column chunk
-              uint32_t mw = 0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
-              __stcs(st.mask + ((size_t)g * st.Mpad + m) * 8 + cb, mw);
-            }
+            side_work(cb, v);
           }
         }
         tc_fence_before();

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         g_s = g.w * density_act_grad(rec.s, a.flags);
         if (half == 0) P.dyc[m] = make_float4(gyc0, gyc1, gyc2, g_s);          // fp32 side stash stays unscaled
         gyc0 *= gscale; gyc1 *= gscale; gyc2 *= gscale; g_s *= gscale;
-        const float* hr = P.hr + m * 128;
+        const uint4 hm = __ldg(reinterpret_cast<const uint4*>(P.mask + ((size_t)8 * P.Mpad + m) * 8));   // sign bits of the rgb hidden layer
         float* dyr = P.dyr + m * 128;
         // dY operand planes of the weight-gradient pass ([hi|lo][sample half][feature block][64 samples][8] bf16) are
         // streamed from registers next to the shared-memory image (the bulk-copy engine stays free for the weight ring)
@@ -277,12 +277,13 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
 #pragma unroll 1
         for (int ji = 0; ji < 8; ++ji) {
           const int jb = 2 * ji + half;       // halves interleave 8-column groups: 64-column block b is done after ji = 4b+3
-          float4 h0 = *reinterpret_cast<const float4*>(hr + jb * 8), h1 = *reinterpret_cast<const float4*>(hr + jb * 8 + 4);
-          float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w}, v[8];
+          const int wq = jb >> 2;
+          const uint32_t mb = (wq == 0 ? hm.x : wq == 1 ? hm.y : wq == 2 ? hm.z : hm.w) >> ((jb & 3) * 8);
+          float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float x = gyc0 * s_small[jb * 8 + j] + gyc1 * s_small[128 + jb * 8 + j] + gyc2 * s_small[256 + jb * 8 + j];
-            v[j] = hv[j] > 0.f ? x : 0.f;
+            v[j] = ((mb >> j) & 1u) ? x : 0.f;
           }
           split_store8_bf16_dual(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16, gpl ? gpl + jb * 1024 : nullptr, gpl + 32768 + jb * 1024);
           *reinterpret_cast<float4*>(dyr + jb * 8) = make_float4(v[0] * inv_gscale, v[1] * inv_gscale, v[2] * inv_gscale, v[3] * inv_gscale);

@@ -17,7 +17,7 @@ struct WsLayout {
   size_t n_tiles;
   size_t xp[10];    // X planes: 0 = enc (64 feat), 1..8 = h0..h7, 9 = feat
   size_t dyp[10];   // dY planes: 0..7 = dy0..dy7, 8 = dfeat, 9 = dyr (128 feat)
-  size_t mask;      // uint32 [8 layers][Mpad][8]
+  size_t mask;      // uint32 [9 layers][Mpad][8]: ReLU sign bits of h0..h7 and (slot 8, 4 words) of the rgb hidden layer
   size_t gmax;      // uint32 bits of max |g| (gradient scaling)
   size_t total;  // bytes
 };
@@ -46,7 +46,7 @@ inline WsLayout make_layout(int N, int S, uint32_t flags, int engine) {
       for (int i = 1; i < 10; ++i) L.xp[i] = take(L.n_tiles * PLANE_TILE_256);
       for (int i = 0; i < 9; ++i) L.dyp[i] = take(L.n_tiles * PLANE_TILE_256);
       L.dyp[9] = take(L.n_tiles * PLANE_TILE_128);
-      L.mask = take(L.Mpad * 8 * 8 * 4);
+      L.mask = take(L.Mpad * 9 * 8 * 4);
       L.gmax = take(256);
     } else {  // fp32 [sample][feature] stash (SIMT backward; also consumed after a TC forward)
       for (int l = 0; l < 8; ++l) L.h[l] = take(L.Mpad * 256 * 4);
