@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           if (planes && (g < 8 || g == 9) && !(dbg & 2)) {   // ReLU bitmask of this 32-column chunk (g = 9: rgb hidden layer, slot 8)
             uint32_t mw = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mw |= (v[j] > 0.f ? 1u : 0u) << j;
+            for (int j = 0; j < 32; ++j) mw |= min(__float_as_uint(v[j]), 1u) << j;   // v = max(x, 0): v > 0 <=> its bits are non-zero
             __stcs(st.mask + ((size_t)(g < 8 ? g : 8) * st.Mpad + m) * 8 + cb, mw);
           }
         };

@@ -254,6 +254,17 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
     unsigned char* A_hi = smem + DG_AHI; unsigned char* A_lo = smem + DG_ALO;
     const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo);
     int tv = -1;
+    // per-row inputs of the prologue, fetched one tile ahead (their global-memory latency hides under the previous tile)
+    float4 g_pf = make_float4(0.f, 0.f, 0.f, 0.f); SampleRec rec_pf; uint4 hm_pf = make_uint4(0u, 0u, 0u, 0u);
+    auto prefetch_rows = [&](int tile_n) {
+      const size_t mn = (size_t)tile_n * TILE + row;
+      g_pf = (mn < M) ? __ldg(P.gs + mn) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* rp = reinterpret_cast<const float4*>(P.rec + mn);
+      const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+      rec_pf.r = r0.x; rec_pf.g = r0.y; rec_pf.b = r0.z; rec_pf.a = r0.w; rec_pf.s = r1.x; rec_pf.z = r1.y; rec_pf.pad0 = r1.z; rec_pf.pad1 = r1.w;
+      hm_pf = __ldg(reinterpret_cast<const uint4*>(P.mask + ((size_t)8 * P.Mpad + mn) * 8));   // sign bits of the rgb hidden layer
+    };
+    if ((int)blockIdx.x < n_tiles) prefetch_rows(blockIdx.x);
     for (int tt = 0; tt < my_tiles; ++tt) {
       const int tile = blockIdx.x + tt * gridDim.x;
       if (tile >= n_tiles) continue;
@@ -263,13 +274,13 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       epi_bar();
       float g_s;
       {
-        float4 g = (m < M) ? P.gs[m] : make_float4(0.f, 0.f, 0.f, 0.f);
-        SampleRec rec = P.rec[m];
+        const float4 g = g_pf;
+        const SampleRec rec = rec_pf;
+        const uint4 hm = hm_pf;
         float gyc0 = g.x * rec.r * (1.f - rec.r), gyc1 = g.y * rec.g * (1.f - rec.g), gyc2 = g.z * rec.b * (1.f - rec.b);
         g_s = g.w * density_act_grad(rec.s, a.flags);
         if (half == 0) P.dyc[m] = make_float4(gyc0, gyc1, gyc2, g_s);          // fp32 side stash stays unscaled
         gyc0 *= gscale; gyc1 *= gscale; gyc2 *= gscale; g_s *= gscale;
-        const uint4 hm = __ldg(reinterpret_cast<const uint4*>(P.mask + ((size_t)8 * P.Mpad + m) * 8));   // sign bits of the rgb hidden layer
         float* dyr = P.dyr + m * 128;
         // dY operand planes of the weight-gradient pass ([hi|lo][sample half][feature block][64 samples][8] bf16) are
         // streamed from registers next to the shared-memory image (the bulk-copy engine stays free for the weight ring)
@@ -296,12 +307,15 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       for (int pos = 0; pos < N_POS; ++pos) {
         const int buf = pos & 1;
         const uint32_t use = buf ? (uint32_t)t * 5u + (uint32_t)(pos >> 1) : (uint32_t)t * 6u + (uint32_t)(pos >> 1);
-        mbar_wait(BAR(D_ACCFULL + buf), use & 1u);
-        tc_fence_after();
         const bool writes_a = (pos != 5 && pos != 10);
         // mask layer: g_y_l = g_h_l * (h_l > 0) with l = 7 (pos1), 6,5,4 (pos2..4), 3 (pos6), 2,1,0 (pos7..9)
         const int mask_l = (pos == 1) ? 7 : (pos >= 2 && pos <= 4) ? 8 - pos : (pos == 6) ? 3 : (pos >= 7 && pos <= 9) ? 9 - pos : -1;
         const uint32_t* mrow = (mask_l >= 0) ? P.mask + ((size_t)mask_l * P.Mpad + m) * 8 : nullptr;
+        // this thread's four mask words (chunks half, 2+half, 4+half, 6+half): loaded BEFORE the accumulator wait
+        uint32_t mq0 = 0xffffffffu, mq1 = 0xffffffffu, mq2 = 0xffffffffu, mq3 = 0xffffffffu;
+        if (mrow) { mq0 = __ldg(mrow + half); mq1 = __ldg(mrow + 2 + half); mq2 = __ldg(mrow + 4 + half); mq3 = __ldg(mrow + 6 + half); }
+        mbar_wait(BAR(D_ACCFULL + buf), use & 1u);
+        tc_fence_after();
         const int nch = (pos == 5 || pos == 10) ? 1 : 4;   // 32-column chunks handled by this half
         // A will hold: pos0 -> g_feat ; pos1 -> g_y7 ; pos2..4 -> g_y6..4 ; pos6 -> g_y3 ; pos7..9 -> g_y2..0
         const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           uint32_t r[32];
           tc_ld32(lane_addr + buf * 256 + cb * 32, r);
           float v[32];
-          const uint32_t mw = mrow ? __ldg(mrow + cb) : 0xffffffffu;
+          const uint32_t mw = (ci == 0) ? mq0 : (ci == 1) ? mq1 : (ci == 2) ? mq2 : mq3;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]);
@@ -340,13 +354,37 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         tc_fence_before();
         mbar_arrive(BAR(D_ACCEMPTY + buf));
       }
-      // ---- encoding adjoint (both halves' columns of g_enc are in shared memory) ----
+      // ---- encoding adjoint (both halves' columns of g_enc are in shared memory): half 0 takes the raw coordinates and
+      //      levels 0..4, half 1 levels 5..9; half 1 hands its partial sum over through its own (consumed) g_enc slots ----
+      if (tile + (int)gridDim.x < n_tiles) prefetch_rows(tile + (int)gridDim.x);
       epi_bar();
-      if (half == 0) {
+      {
         Ray ray; int n, i; float z, p[3], gp[3];
         row_geometry_b(a, m, M, ray, n, i, z, p);
-        encode_bwd<10>(p, [&](int k) { return s_genc[k * 128 + row]; }, gp);
-        P.gp[m] = make_float4(gp[0] * inv_gscale, gp[1] * inv_gscale, gp[2] * inv_gscale, 0.f);
+        float f = half ? 32.f : 1.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gp[c] = half ? 0.f : s_genc[c * 128 + row];
+#pragma unroll
+        for (int l5 = 0; l5 < 5; ++l5) {
+          const int l = half * 5 + l5;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, co;
+            sincosf(__fmul_rn(f, p[c]), &sn, &co);
+            gp[c] += f * (co * s_genc[(3 + 6 * l + c) * 128 + row] - sn * s_genc[(6 + 6 * l + c) * 128 + row]);
+          }
+          f *= 2.f;
+        }
+        if (half == 1) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) s_genc[(60 + c) * 128 + row] = gp[c];
+        }
+        epi_bar();
+        if (half == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) gp[c] += s_genc[(60 + c) * 128 + row];
+          P.gp[m] = make_float4(gp[0] * inv_gscale, gp[1] * inv_gscale, gp[2] * inv_gscale, 0.f);
+        }
       }
     }
   }
