@@ -216,15 +216,11 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             const uint32_t wb = smem_u32(smem + SM_W + slot * STAGE_BYTES);
             const uint64_t dAh = make_desc(ahi, 2048, 128), dAl = make_desc(alo, 2048, 128);
             const uint64_t dBh = make_desc(wb, b_lbo, 128), dBl = make_desc(wb + N * 32, b_lbo, 128);
-            tc_mma_f16(d_tmem, dAl, dBh, idesc, acc);
-            tc_mma_f16(d_tmem, dAh, dBl, idesc, 1u);
-            tc_mma_f16(d_tmem, dAh, dBh, idesc, 1u);
-            acc = 1u;
-            {   // probe the NEXT stage's barrier before committing: the round trip overlaps the MMA issue / commit
+            {   // the NEXT stage's barrier is probed inside the same instruction group: its round trip overlaps the MMA issue / commit
               const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
-              full_ok = mbar_probe(BAR(B_FULL + nslot), nphase);
+              full_ok = tc_stage_mma3<CL>(d_tmem, dAl, dAh, dBh, dBl, idesc, acc, BAR(B_EMPTY + slot), cmask, BAR(B_FULL + nslot), nphase);
             }
-            if (CL == 1) tc_commit(BAR(B_EMPTY + slot)); else tc_commit_mc(BAR(B_EMPTY + slot), cmask);
+            acc = 1u;
             if (++slot == NST) { slot = 0; phase ^= 1; }
             PROF_ADD(4);
           }

@@ -229,15 +229,11 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
             const uint32_t wb = smem_u32(smem + DG_W + slot * STAGE_BYTES);
             const uint64_t dAh = make_desc(a_hi + ks * 4096, 2048, 128), dAl = make_desc(a_lo + ks * 4096, 2048, 128);
             const uint64_t dBh = make_desc(wb, b_lbo, 128), dBl = make_desc(wb + N * 32, b_lbo, 128);
-            tc_mma_f16(d_tmem, dAl, dBh, idesc, acc);
-            tc_mma_f16(d_tmem, dAh, dBl, idesc, 1u);
-            tc_mma_f16(d_tmem, dAh, dBh, idesc, 1u);
-            acc = 1u;
             {
               const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
-              full_ok = mbar_probe(BAR(D_FULL + nslot), nphase);
+              full_ok = tc_stage_mma3<CL>(d_tmem, dAl, dAh, dBh, dBl, idesc, acc, BAR(D_EMPTY + slot), cmask, BAR(D_FULL + nslot), nphase);
             }
-            if (CL == 1) tc_commit(BAR(D_EMPTY + slot)); else tc_commit_mc(BAR(D_EMPTY + slot), cmask);
+            acc = 1u;
             if (++slot == NST) { slot = 0; phase ^= 1; }
           }
           tc_commit(BAR(D_ACCFULL + buf));

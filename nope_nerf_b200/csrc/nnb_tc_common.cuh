@@ -173,6 +173,44 @@ __device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint3
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {   // arrive on `bar` in every CTA of `mask`
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
+// One weight stage of the split-precision GEMM chains: probe the NEXT stage's "full" barrier, issue the three MMAs
+// (a_lo*b_hi [+ optional restart of the accumulator], a_hi*b_lo, a_hi*b_hi), commit the stage's "empty" barrier, and only
+// then read the probe's predicate -- the ~110-cycle barrier round trip hides under the MMA issue.
+template <int CL>
+__device__ __forceinline__ uint32_t tc_stage_mma3(uint32_t d_tmem, uint64_t a_lo, uint64_t a_hi, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                                  uint32_t acc, uint32_t empty_bar, uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
+  uint32_t ok;
+  if (CL == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %4, %6, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %5, %6, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, t;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ok)
+        : "r"(d_tmem), "l"(a_lo), "l"(a_hi), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %4, %6, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %5, %6, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, t;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], %11;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ok)
+        : "r"(d_tmem), "l"(a_lo), "l"(a_hi), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask)
+        : "memory");
+  }
+  return ok;
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 }  // namespace tcu
 
