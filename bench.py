@@ -14,8 +14,9 @@ full backward (MLP + pose + depth-distortion gradients), [all-reduce], optimizer
   e2e   : same step through the reference-facing API with HOST (page-locked) frame tensors, as train.py's DataLoader
           (pin_memory=True) hands them over: host->device traffic (DPT map copy + in-place gather of the sampled
           pixels over PCIe) and the D2H read of the loss every step (train.py:212) are inside the timed region.
-  N > 1 : strong scaling — the SAME 1024-ray batch is sharded rank::N (Trainer dp_mode='rays'), ONE
-          NCCL all-reduce of the flat [gradients | loss] buffer per step.
+  N > 1 : weak scaling — every GPU keeps the C2 per-GPU work (1024 rays x 128 samples): the step draws a global batch of
+          1024*N rays, sharded rank::N (Trainer dp_mode='rays'), ONE NCCL all-reduce of the flat [gradients | loss]
+          buffer per step; value = all ranks' ray-samples / max-over-ranks time.
   --impl reference : the reference's own CPU path for the same step (the numpy oracle port, all host
           threads; /root/reference itself is Python and does not travel to the GPU box).
 """
@@ -87,7 +88,7 @@ def make_cfg():
     from _cfg import default_cfg
     cfg = default_cfg()
     cfg["training"]["pc_weight"] = [0.0, 0.0]; cfg["training"]["rgb_s_weight"] = [0.0, 0.0]   # render + rgb + depth losses
-    cfg["training"]["n_training_points"] = NRAYS; cfg["rendering"]["num_points"] = S
+    cfg["training"]["n_training_points"] = NRAYS * int(os.environ.get("WORLD_SIZE", 1)); cfg["rendering"]["num_points"] = S
     return cfg
 
 
@@ -194,8 +195,8 @@ def run_ours(args):
     ms_e2e, _ = timed(host, K, 2, sync_loss=True)
     if rank == 0:
         pk = peaks()
-        n_local = NRAYS // world
-        samples_per_step = NRAYS * S
+        n_local = NRAYS                              # weak scaling: per-GPU work fixed, global batch = NRAYS * world
+        samples_per_step = NRAYS * world * S
         value = samples_per_step * K / (ms / 1e3)
         e2e = samples_per_step * K / (ms_e2e / 1e3)
         # roofline of the dominant kernel (largest average duration in the profiled pass)
@@ -210,17 +211,20 @@ def run_ours(args):
                     "kernel_ms": {k: round(v, 4) for k, v in prof.items()},
                     "note": "algorithmic fp32-equivalent FLOPs; the tcgen05 engine issues 3 fp16 MMAs per logical product"}
         line = {"metric": "train-step ray-samples/sec", "value": round(value, 1), "unit": "ray-samples/s", "n_gpus": world, "steps": K,
-                "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "fp32 (split-fp16 tcgen05 MMAs, fp32 accumulate)" if args.engine == "tc" else "fp32", "data": "synthetic",
                 "config": {"workload": "C2 Ignatius-shape 1080x1920, V=200, 1024 rays x 128 samples, uniform+jitter, rgb L1 + depth L1, Adam x3",
-                           "global_rays": NRAYS, "samples_per_ray": S, "parallelism": "dp%d (ray shards, 1 all-reduce)" % world,
+                           "global_rays": NRAYS * world, "rays_per_gpu": NRAYS, "samples_per_ray": S,
+                           "parallelism": "dp%d (ray shards, 1 all-reduce)" % world,
                            "engine": args.engine, "frames_resident": N_FRAMES, "cuda_graph": bool(trainer.use_cuda_graph),
                            "l2_policy": "no flush: each step streams a 2.6 GB activation stash, far larger than the 126 MB L2"},
                 "e2e": {"value": round(e2e, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / K, 4),
-                        "h2d_bytes_per_step": int(NRAYS * 3 * 32 + HD * WD * 4 + 64 + 16), "d2h_bytes_per_step": 4,
+                        "h2d_bytes_per_step": int(NRAYS * 3 * 32 + HD * WD * 4 + 64 + 16) * world, "d2h_bytes_per_step": 4 * world,
                         "h2d_note": "host frames are page-locked: the loss kernel gathers the 1024x3 sampled pixels in place over PCIe "
                                     "(one 32-B sector each) instead of copying the 24.9 MB frame; the 1 MB DPT map, camera_mat and idx are copied"},
-                "gpu_launches": 14 * K, "clocks": clocks, "roofline": roof,
+                # per step and rank: distortion fwd/bwd, pixel sampler, pose fwd/bwd, 2 weight imagers, field fwd, 2 compositing,
+                # loss, dgrad, wgrad, head_wgrad, ray_dir_grad, ray_bwd, counter, 5 Adam launches
+                "gpu_launches": 22 * K * world, "clocks": clocks, "roofline": roof,
                 "loss": float(ld["loss"].item()), "impl": "ours"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sample_rays=256, steps=2)
@@ -262,7 +266,7 @@ def run_reference(args):
     sample = 256
     cb = cpu_baseline(sample, K, warm=max(1, min(Wm, 2)))
     line = {"metric": "train-step ray-samples/sec", "value": cb["value"], "unit": "ray-samples/s", "n_gpus": args.gpus, "steps": K, "warmup": Wm,
-            "ms_per_step": round(cb["sec_per_step"] * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32",
+            "ms_per_step": round(cb["sec_per_step"] * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": "C2 Ignatius-shape 1080x1920, V=200, 1024 rays x 128 samples, uniform+jitter, rgb L1 + depth L1, Adam",
                        "note": "reference CPU path = numpy restatement (oracle/nerf_oracle.py, pinned to the reference by tests/golden); "

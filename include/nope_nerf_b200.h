@@ -125,7 +125,7 @@ int nnb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
                       float beta2, float eps, void* stream);
 int nnb_counter_incr(int32_t* counters, int32_t n, void* stream);
 /* N distinct pixel ids uniform in [0,HW) from 2N uniforms u in [0,1): same distribution as torch.randperm(HW)[:N]
- * (model/training.py:257) without sorting HW keys. */
+ * (model/training.py:257) without sorting HW keys.  0 < N <= min(HW/2, 8192). */
 int nnb_sample_pixels(const float* u2n, int32_t HW, int32_t N, int64_t* out, void* stream);
 int nnb_loss_rgb_depth_indirect(const float* rgb, const float* const* img_pp /* device pointer to the frame pointer */, const int64_t* ray_idx,
                                 int32_t HW, const float* depth_pred, const float* depth_gt, const uint8_t* mask, int32_t N, float w_rgb,

@@ -176,7 +176,7 @@ int nnb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_adam_step_dev");
 }
 int nnb_sample_pixels(const float* u2n, int32_t HW, int32_t N, int64_t* out, void* stream) {
-  if (!u2n || !out || HW <= 0 || N <= 0 || N > HW / 2 || N > 4096) return fail(-3, "nnb_sample_pixels: bad arguments (need 0 < N <= min(HW/2, 4096))");
+  if (!u2n || !out || HW <= 0 || N <= 0 || N > HW / 2 || N > 8192) return fail(-3, "nnb_sample_pixels: bad arguments (need 0 < N <= min(HW/2, 8192))");
   cudaError_t e = launch_sample_pixels(u2n, HW, N, reinterpret_cast<long long*>(out), (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_sample_pixels");
 }

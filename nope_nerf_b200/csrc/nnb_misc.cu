@@ -283,6 +283,7 @@ cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, int64_
 }
 cudaError_t launch_sample_pixels(const float* u, int HW, int N, long long* out, cudaStream_t st) {
   int tsize = 1024; while (tsize < 4 * N) tsize <<= 1;
+  if (((size_t)2 * tsize + N) * 4 > 200 * 1024) tsize >>= 1;     // N in (4096, 8192]: load factor 1/2 still fits 200 KB
   size_t smem = ((size_t)2 * tsize + N) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static bool attr = false;

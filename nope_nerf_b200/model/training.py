@@ -195,7 +195,7 @@ class _GraphStep:
         g_c2w = self.small[:16].view(4, 4); g_ss = self.small[16:18]
         ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx, dnet.fix_scaleN, self.ss)
         n_points = tr.n_training_points
-        if tr.pixel_sampler == 'randperm' or (tr.pixel_sampler == 'auto' and not tr.use_cuda_graph) or n_points > min(h * w // 2, 4096):
+        if tr.pixel_sampler == 'randperm' or (tr.pixel_sampler == 'auto' and not tr.use_cuda_graph) or n_points > min(h * w // 2, 8192):
             ray_idx = torch.randperm(h * w, device=dev)[:n_points]                # training.py:257 (reference RNG stream)
         else:
             ray_idx = ops.sample_pixels(h * w, n_points, dev)                     # same distribution, no 2M-key sort

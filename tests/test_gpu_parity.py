@@ -485,3 +485,5 @@ def test_pixel_sampler_distinct_and_uniform():
     assert np.abs(frac - 1 / 16).max() < 0.01            # 51 200 draws over 16 bins: sigma ~ 0.001
     small = ops.sample_pixels(4096, 2048, "cuda")        # dense case exercises the duplicate / probing paths
     assert torch.unique(small).numel() == 2048
+    big = ops.sample_pixels(HW, 8192, "cuda")            # largest batch the in-graph sampler serves (8 GPUs x 1024 rays)
+    assert big.min() >= 0 and big.max() < HW and torch.unique(big).numel() == 8192
