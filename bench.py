@@ -16,7 +16,8 @@ full backward (MLP + pose + depth-distortion gradients), [all-reduce], optimizer
           pixels over PCIe) and the D2H read of the loss every step (train.py:212) are inside the timed region.
   N > 1 : weak scaling — every GPU keeps the C2 per-GPU work (1024 rays x 128 samples): the step draws a global batch of
           1024*N rays, sharded rank::N (Trainer dp_mode='rays'), ONE NCCL all-reduce of the flat [gradients | loss]
-          buffer per step; value = all ranks' ray-samples / max-over-ranks time.
+          buffer per step; value = all ranks' ray-samples / max-over-ranks time.  --scaling strong splits the 1024-ray
+          batch over the GPUs instead (128 tiles per GPU at N=8: launch-bound).
   --impl reference : the reference's own CPU path for the same step (the numpy oracle port, all host
           threads; /root/reference itself is Python and does not travel to the GPU box).
 """
@@ -34,6 +35,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 H, W, HD, WD, V, NRAYS, S = 1080, 1920, 384, 672, 200, 1024, 128
+WEAK = True                       # --scaling weak (default): 1024 rays per GPU; strong: the same 1024-ray batch split over the GPUs
 N_FRAMES = 8                      # distinct synthetic frames cycled through (each 24.9 MB + 1 MB DPT map)
 FLOP_PER_SAMPLE_STEP = 3560448    # fwd + dgrad + wgrad
 FLOP_PER_SAMPLE_FWD = 1186816
@@ -88,7 +90,7 @@ def make_cfg():
     from _cfg import default_cfg
     cfg = default_cfg()
     cfg["training"]["pc_weight"] = [0.0, 0.0]; cfg["training"]["rgb_s_weight"] = [0.0, 0.0]   # render + rgb + depth losses
-    cfg["training"]["n_training_points"] = NRAYS * int(os.environ.get("WORLD_SIZE", 1)); cfg["rendering"]["num_points"] = S
+    cfg["training"]["n_training_points"] = NRAYS * (int(os.environ.get("WORLD_SIZE", 1)) if WEAK else 1); cfg["rendering"]["num_points"] = S
     return cfg
 
 
@@ -195,8 +197,8 @@ def run_ours(args):
     ms_e2e, _ = timed(host, K, 2, sync_loss=True)
     if rank == 0:
         pk = peaks()
-        n_local = NRAYS                              # weak scaling: per-GPU work fixed, global batch = NRAYS * world
-        samples_per_step = NRAYS * world * S
+        n_local = NRAYS if WEAK else NRAYS // world     # weak scaling: per-GPU work fixed, global batch = NRAYS * world
+        samples_per_step = n_local * world * S
         value = samples_per_step * K / (ms / 1e3)
         e2e = samples_per_step * K / (ms_e2e / 1e3)
         # roofline of the dominant kernel (largest average duration in the profiled pass)
@@ -211,15 +213,15 @@ def run_ours(args):
                     "kernel_ms": {k: round(v, 4) for k, v in prof.items()},
                     "note": "algorithmic fp32-equivalent FLOPs; the tcgen05 engine issues 3 fp16 MMAs per logical product"}
         line = {"metric": "train-step ray-samples/sec", "value": round(value, 1), "unit": "ray-samples/s", "n_gpus": world, "steps": K,
-                "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak" if WEAK else "strong", "vs_baseline": None,
                 "dtype": "fp32 (split-fp16 tcgen05 MMAs, fp32 accumulate)" if args.engine == "tc" else "fp32", "data": "synthetic",
                 "config": {"workload": "C2 Ignatius-shape 1080x1920, V=200, 1024 rays x 128 samples, uniform+jitter, rgb L1 + depth L1, Adam x3",
-                           "global_rays": NRAYS * world, "rays_per_gpu": NRAYS, "samples_per_ray": S,
+                           "global_rays": n_local * world, "rays_per_gpu": n_local, "samples_per_ray": S,
                            "parallelism": "dp%d (ray shards, 1 all-reduce)" % world,
                            "engine": args.engine, "frames_resident": N_FRAMES, "cuda_graph": bool(trainer.use_cuda_graph),
                            "l2_policy": "no flush: each step streams a 2.6 GB activation stash, far larger than the 126 MB L2"},
                 "e2e": {"value": round(e2e, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / K, 4),
-                        "h2d_bytes_per_step": int(NRAYS * 3 * 32 + HD * WD * 4 + 64 + 16) * world, "d2h_bytes_per_step": 4 * world,
+                        "h2d_bytes_per_step": int(n_local * 3 * 32 + HD * WD * 4 + 64 + 16) * world, "d2h_bytes_per_step": 4 * world,
                         "h2d_note": "host frames are page-locked: the loss kernel gathers the 1024x3 sampled pixels in place over PCIe "
                                     "(one 32-B sector each) instead of copying the 24.9 MB frame; the 1 MB DPT map, camera_mat and idx are copied"},
                 # per step and rank: distortion fwd/bwd, pixel sampler, pose fwd/bwd, 2 weight imagers, field fwd, 2 compositing,
@@ -283,7 +285,10 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 1024 rays per GPU (global batch 1024*N), strong = the 1024-ray batch split over the GPUs")
     a = ap.parse_args()
+    WEAK = (a.scaling == "weak")
     if a.impl == "reference":
         run_reference(a)
     else:
