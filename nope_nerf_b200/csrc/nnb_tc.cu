@@ -7,10 +7,11 @@
 //                 (M=128, N=256|128, K=16) with BOTH operands from shared memory; every logical
 //                 product runs as three MMAs a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (split-fp16, 22-bit
 //                 operands, fp32 accumulation in TMEM) so results match the fp32 reference
-//   warps 2..5  : epilogue         - tcgen05.ld of the accumulator (thread = sample row), bias +
-//                 ReLU, re-split into hi/lo halves written IN PLACE as the next layer's A operand
-//                 (canonical no-swizzle K-major core-matrix layout), density / colour heads,
-//                 activation stash for the backward pass.
+//   warps 2..9  : epilogue         - two warps per TMEM lane quarter (thread = sample row, the two warps take
+//                 alternate 32-column chunks): tcgen05.ld of the accumulator, bias + ReLU, re-split into
+//                 hi/lo halves written IN PLACE as the next layer's A operand (canonical no-swizzle
+//                 K-major core-matrix layout); then, from the same registers, density / colour heads and
+//                 the training stash (bf16 operand planes, ReLU bitmasks, fp32 side stash).
 //
 // Two 256-column TMEM accumulators alternate between consecutive layers and the A operand becomes
 // ready in 64-column blocks (one mbarrier each), so layer l+1's MMAs start while layer l's epilogue

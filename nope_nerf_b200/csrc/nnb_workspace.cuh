@@ -12,8 +12,9 @@ struct WsLayout {
   // SIMT engine activation stash (fp32, [sample][feature])
   size_t h[8], feat, hr, enc, denc;
   size_t dy[8], dfeat, dyr, dyc;
-  // tcgen05 backward (NNB_TCBWD): activations / output-gradients as per-tile fp16 hi|lo operand images
-  // ("planes": [tile][hi|lo][feature/8][128 samples][8 features]) + ReLU bitmasks
+  // tcgen05 backward (NNB_TCBWD): activations / output-gradients as per-tile bf16 hi|lo operand planes
+  // ([tile][hi|lo][sample half][feature/8][64 samples][8 features]: every 64-sample half of a plane is one contiguous
+  // bulk copy for tc_wgrad and an MN-major tcgen05 operand as it lands) + ReLU bitmasks
   size_t n_tiles;
   size_t xp[10];    // X planes: 0 = enc (64 feat), 1..8 = h0..h7, 9 = feat
   size_t dyp[10];   // dY planes: 0..7 = dy0..dy7, 8 = dfeat, 9 = dyr (128 feat)
