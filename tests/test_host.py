@@ -156,3 +156,29 @@ def test_data_parallel_shard_arithmetic_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_resident_dataset_views_and_reference_frames():
+    """frames live in one resident store, __getitem__ hands out views under the reference's keys"""
+    import random
+    from nope_nerf_b200.dataloading import ResidentDataset
+    V, H, W, hd, wd = 5, 12, 16, 6, 8
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(V, 3, H, W, generator=g); dpts = torch.rand(V, hd, wd, generator=g) + 0.5
+    K = torch.diag(torch.tensor([1.2, -1.6, -1.0, 1.0]))
+    ds = ResidentDataset(imgs, dpts, K, device="cpu", load_ref_img=True, random_ref=2, pin_host=False)
+    assert len(ds) == V
+    item = ds[3]
+    assert set(item) == {"img", "img.idx", "img.dpt", "img.camera_mat", "img.scale_mat", "img.ref_imgs", "img.ref_dpts", "img.ref_idxs"}
+    assert item["img"].shape == (1, 3, H, W) and item["img.dpt"].shape == (1, hd, wd) and item["img.camera_mat"].shape == (1, 4, 4)
+    assert item["img"].data_ptr() == ds.imgs[3].data_ptr() and item["img.dpt"].data_ptr() == ds.dpts[3].data_ptr()   # views, not copies
+    assert torch.equal(item["img"][0], imgs[3]) and int(item["img.idx"]) == 3
+    assert int(item["img.ref_idxs"]) == 4 and torch.equal(item["img.ref_imgs"][0], imgs[4])      # only one later view left
+    assert int(ds[V - 1]["img.ref_idxs"]) == V - 2                                               # last view looks back (dataset.py:170-171)
+    random.seed(1)
+    refs = {int(ds[0]["img.ref_idxs"]) for _ in range(40)}
+    assert refs == {1, 2}                                                                        # idx + randint(1, min(random_ref, V-idx-1))
+    seen = [int(b["img.idx"]) for b in ds.batches(shuffle=True, generator=torch.Generator().manual_seed(3))]
+    assert sorted(seen) == list(range(V))
+    with pytest.raises(ValueError):
+        ResidentDataset(imgs[:, :2], dpts, K, device="cpu")
