@@ -52,6 +52,31 @@ def exp_so3(r):   # common.py:277-330
     return torch.eye(3, device=r.device, dtype=r.dtype) + (torch.sin(n) / n) * K + ((1 - torch.cos(n)) / n ** 2) * (K @ K)
 
 
+def c2w_of(r, t, cam_id):
+    R = exp_so3(r[cam_id])
+    return torch.cat([torch.cat([R, t[cam_id][:, None]], 1), torch.tensor([[0., 0, 0, 1]], device=r.device)], 0)
+
+
+def render_eval(net, c2w, H, W, kx, ky, S, near, far, chunk=8192):
+    """all pixels of one view, no jitter, eval-mode outputs (rgb (H,W,3), distance along the normalised ray / |d~| = depth)"""
+    dev = c2w.device
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    pix = torch.stack([2.0 * xs.reshape(-1) / (W - 1) - 1.0, 2.0 * ys.reshape(-1) / (H - 1) - 1.0], -1)
+    out_rgb, out_d = [], []
+    with torch.no_grad():
+        for i in range(0, H * W, chunk):
+            p = pix[i:i + chunk]; n = p.shape[0]
+            dcam = torch.stack([p[:, 0] / kx, p[:, 1] / ky, -torch.ones(n, device=dev)], -1)
+            dt = dcam @ c2w[:3, :3].t(); nrm = dt.norm(dim=-1, keepdim=True); d = dt / nrm
+            u = torch.linspace(0, 1, S, device=dev); z = (near * (1 - u) + far * u).expand(n, S)
+            pts = (c2w[:3, 3].expand(n, 3)[:, None] + d[:, None] * z[..., None]).reshape(-1, 3)
+            rgb_s, alpha = net(pts, (-d)[:, None].expand(n, S, 3).reshape(-1, 3))
+            alpha = alpha.reshape(n, S)
+            w = alpha * torch.cumprod(torch.cat([torch.ones(n, 1, device=dev), 1 - alpha + 1e-6], -1), -1)[:, :-1]
+            out_rgb.append((w[..., None] * rgb_s.reshape(n, S, 3)).sum(1)); out_d.append((w * z).sum(1) / nrm[:, 0])
+    return torch.cat(out_rgb).reshape(H, W, 3), torch.cat(out_d).reshape(H, W)
+
+
 def step(net, r, t, scales, shifts, opts, img, dpt, cam_id, kx, ky, N, S, near, far, ray_idx=None, noise=None):
     H, W = img.shape[-2:]; dev = img.device
     for o in opts: o.zero_grad()
