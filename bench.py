@@ -39,6 +39,10 @@ WEAK = True                       # --scaling weak (default): 1024 rays per GPU;
 N_FRAMES = 8                      # distinct synthetic frames cycled through (each 24.9 MB + 1 MB DPT map)
 FLOP_PER_SAMPLE_STEP = 3560448    # fwd + dgrad + wgrad
 FLOP_PER_SAMPLE_FWD = 1186816
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 1024 x 128 samples, from the committed `ncu --set full` capture
+# (profiles/ncu_r1_final_tc_kernels_summary.txt); algorithmic HBM bytes of the step are ~5 MB: the rest
+# is the activation stash the backward re-reads
+NCU_DRAM_BYTES = {"field_fwd": 1.451e9, "dgrad": 1.335e9, "wgrad": 2.686e9}
 
 
 def peaks():
@@ -208,7 +212,9 @@ def run_ours(args):
         if dom:
             ach = flops[dom] * (n_local * S) / (prof[dom] / 1e3) / 1e12
             roof = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 2), "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": round(ach / pk["tflops_sustained"], 4), "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                    "frac": round(ach / pk["tflops_sustained"], 4),
+                    "traffic": NCU_DRAM_BYTES.get(dom) if (n_local == NRAYS and args.engine == "tc") else None,
+                    "traffic_source": "profiles/ncu_r1_final_tc_kernels_summary.txt (ncu --set full, bytes per launch)", "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                     "algorithmic_flop_per_launch": flops[dom] * n_local * S,
                     "kernel_ms": {k: round(v, 4) for k, v in prof.items()},
                     "note": "algorithmic fp32-equivalent FLOPs; the tcgen05 engine issues 3 fp16 MMAs per logical product"}
