@@ -94,3 +94,47 @@ def test_render(name):
          np.array([g["grad_scale"], g["grad_shift"]]))
     env = check_param_digest(g, gr64["params"])
     assert check_param_digest(g, gr["params"]) < max(5e-4, floor, 3 * env)
+
+
+def _oracle_train(g, dtype):
+    cfg = dict(O.DEFAULT_CFG); cfg["num_points"] = int(g["S"])
+    state = dict(P={k: v.astype(dtype) for k, v in O.init_params(seed=int(g["seed"])).items()},
+                 r=g["r0"].astype(dtype).copy(), t=g["t0"].astype(dtype).copy(),
+                 scales=g["scales0"].astype(dtype).copy(), shifts=g["shifts0"].astype(dtype).copy())
+    hist = []
+    for it in range(int(g["steps"])):
+        ld, grads, _ = O.train_step(state, g["img"].astype(dtype), g["dpt"].astype(dtype), g["ray_idx_%d" % it], g["noise_%d" % it].astype(dtype),
+                                    int(g["idx"]), dtype(g["kx"]), dtype(g["ky"]), cfg, w_rgb=1.0, w_depth=0.04, rgb_loss_type="l1")
+        hist.append((ld, grads))
+    return state, hist
+
+
+def test_train_step_render_only():
+    """oracle.train_step (the function bench.py times as the CPU baseline and smoke() checks against) vs two consecutive
+    reference Trainer.train_step calls (model/training.py:67-97; render + rgb L1 + depth L1, epoch 0 weights 1.0 / 0.04,
+    torch.optim.Adam x3): losses, pose / distortion / MLP gradients of both steps, and every parameter after the two updates."""
+    g = load_golden("train_render_only")
+    idx = int(g["idx"])
+    st32, h32 = _oracle_train(g, np.float32)
+    st64, h64 = _oracle_train(g, np.float64)
+    for it in range(int(g["steps"])):
+        ld, gr = h32[it]; _, gr64 = h64[it]
+        for k in ("loss", "loss_rgb", "loss_depth", "l2_mean"):
+            ref = float(g["loss_%d.%s" % (it, k)])
+            assert abs(float(ld[k]) - ref) / abs(ref) < 2e-5, (it, k, float(ld[k]), ref)
+        for name, key in (("r", "grad_r_%d"), ("t", "grad_t_%d")):
+            ref = g[key % it][idx]
+            env = relmax(gr64[name], ref)
+            assert relmax(gr[name], ref) < max(2e-4, 3 * env), (it, name, relmax(gr[name], ref), env)
+            assert np.abs(np.delete(g[key % it], idx, 0)).max() == 0.0          # only the current view receives a pose gradient
+        ref_ss = np.array([g["grad_scales_%d" % it][idx, 0], g["grad_shifts_%d" % it][idx, 0]])
+        env = relmax(np.array([gr64["scale"], gr64["shift"]]), ref_ss)
+        assert relmax(np.array([gr["scale"], gr["shift"]]), ref_ss) < max(2e-4, 3 * env)
+        env = check_param_digest(g, gr64["P"], prefix="pg_%d." % it)
+        assert check_param_digest(g, gr["P"], prefix="pg_%d." % it) < max(5e-4, 3 * env), it
+    # Adam: parameters after the two updates (differences are measured on the UPDATE, which is ~lr in size)
+    for key in ("r", "t", "scales", "shifts"):
+        upd_ref = g[key + "_end"] - g[key + "0"]
+        assert relmax(st32[key] - g[key + "0"], upd_ref) < 2e-3, key
+    env = check_param_digest(g, st64["P"], prefix="pend.")
+    assert check_param_digest(g, st32["P"], prefix="pend.") < max(1e-5, 3 * env)
