@@ -138,3 +138,14 @@ def test_train_step_render_only():
         assert relmax(st32[key] - g[key + "0"], upd_ref) < 2e-3, key
     env = check_param_digest(g, st64["P"], prefix="pend.")
     assert check_param_digest(g, st32["P"], prefix="pend.") < max(1e-5, 3 * env)
+
+
+def test_chamfer_dense():
+    """oracle.chamfer vs the reference's Loss.get_pc_loss + autograd (model/losses.py:114-148) on two point clouds with one
+    coincident pair (zero distance: sub-gradient 0) and one duplicated target (argmin tie -> first index)."""
+    g = load_golden("chamfer_dense")
+    loss, gX, gY, ixy, iyx = O.chamfer(g["X"], g["Y"])
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-6
+    assert relmax(gX, g["gX"]) < 1e-5 and relmax(gY, g["gY"]) < 1e-5
+    assert ixy[7] == 5 and not np.any(ixy == 11)          # the coincident pair; the duplicate at 11 never wins against index 3
+    assert np.isfinite(gX).all() and np.isfinite(gY).all()

@@ -269,10 +269,28 @@ def case_train_step(mdl, name, with_ref, steps, N, S, H, W, hd, wd, seed, last_v
     print("wrote", name, {k: float(v) for k, v in ld.items() if hasattr(v, "item") and v.numel() == 1})
 
 
+def case_chamfer(mdl, name, P, Q, seed):
+    """Loss.get_pc_loss 'dense' (model/losses.py:114-148) + autograd on two random point clouds (incl. one exact duplicate pair
+    and one tie, which torch.argmin resolves to the first index)."""
+    import torch
+    from model.losses import Loss
+    cfg = base_cfg()
+    rng = np.random.default_rng(seed)
+    X = rng.normal(0, 1, (P, 3)).astype(np.float32); Y = rng.normal(0, 1, (Q, 3)).astype(np.float32)
+    Y[5] = X[7]                      # zero distance: the norm's sub-gradient is 0 there
+    Y[11] = Y[3]                     # duplicated target: ties -> first index
+    Xt = torch.from_numpy(X)[None].requires_grad_(True); Yt = torch.from_numpy(Y)[None].requires_grad_(True)
+    loss = Loss(cfg["training"]).get_pc_loss(Xt, Yt)
+    loss.backward()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), X=X, Y=Y, loss=np.float32(loss.item()),
+                        gX=Xt.grad[0].numpy(), gY=Yt.grad[0].numpy())
+    print("wrote", name, float(loss))
+
+
 def main():
     mdl = import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    which = sys.argv[1:] or ["mlp", "pose", "render", "train"]
+    which = sys.argv[1:] or ["mlp", "pose", "render", "chamfer", "train"]
     if "mlp" in which:
         case_mlp(mdl, "mlp_alpha_softplus", 96, False, "softplus", 11)
         case_mlp(mdl, "mlp_sigma_relu", 96, True, "relu", 12)
@@ -291,6 +309,8 @@ def main():
         case_render(mdl, "render_oddflags", {"rendering.white_background": True, "rendering.use_ray_dir": False,
                                              "rendering.normalise_ray": False, "model.occ_activation": "relu"},
                     N=32, S=32, H=30, W=40, hd=12, wd=21, eval_mode=False, add_noise=False, seed=25, pose_mode="rand")
+    if "chamfer" in which:
+        case_chamfer(mdl, "chamfer_dense", 193, 160, 41)
     if "train" in which:
         case_train_step(mdl, "train_render_only", False, steps=2, N=48, S=32, H=24, W=32, hd=16, wd=24, seed=31)
         case_train_step(mdl, "train_full_losses", True, steps=2, N=48, S=32, H=24, W=32, hd=16, wd=24, seed=32)
