@@ -482,6 +482,150 @@ def chamfer(X, Y, chunk=2048):
 
 
 # ----------------------------------------------------------------------------
+# Reference-image stage of Trainer.compute_loss (model/training.py:280-365): point-cloud (chamfer)
+# and warped-RGB terms between the current view and one reference view
+# ----------------------------------------------------------------------------
+REF_CFG = dict(nearest_limit=0.01, pc_ratio=4, scale_pcs=True, detach_rgbs_scale=False)   # configs/default.yaml training.*
+
+
+def nearest_resize(d, res):
+    """F.interpolate(d, res, mode='nearest') (training.py:318-319): src = floor(dst * in/out), scale in float32."""
+    hd, wd = d.shape; h, w = res
+    sr = np.minimum(np.floor(np.arange(h, dtype=np.float32) * np.float32(hd / h)).astype(np.int64), hd - 1)
+    sc = np.minimum(np.floor(np.arange(w, dtype=np.float32) * np.float32(wd / w)).astype(np.int64), wd - 1)
+    return d[sr][:, sc], sr, sc
+
+
+def bilinear_resize(img, res):
+    """F.interpolate(img, res, mode='bilinear') with align_corners=False, no antialiasing (training.py:326-327); img (C,H,W)."""
+    C, H, W = img.shape; h, w = res; dt = img.dtype.type
+    def axis(n_out, n_in):
+        src = np.maximum((np.arange(n_out, dtype=img.dtype) + dt(0.5)) * dt(n_in / n_out) - dt(0.5), dt(0))
+        i0 = np.minimum(np.floor(src).astype(np.int64), n_in - 1); i1 = np.minimum(i0 + 1, n_in - 1)
+        return i0, i1, (src - i0.astype(img.dtype)).astype(img.dtype)
+    y0, y1, ly = axis(h, H); x0, x1, lx = axis(w, W)
+    top = img[:, y0][:, :, x0] * (1 - lx) + img[:, y0][:, :, x1] * lx
+    bot = img[:, y1][:, :, x0] * (1 - lx) + img[:, y1][:, :, x1] * lx
+    return top * (1 - ly)[None, :, None] + bot * ly[None, :, None]
+
+
+def grid_sample_bilinear(img, xy, g_out=None):
+    """F.grid_sample(img, xy, mode='bilinear', padding_mode='zeros', align_corners=True) for img (C,h,w), xy (P,2) in [-1,1]
+    (get_tensor_values, model/common.py:75-109).  Returns values (P,C); with g_out (P,C) also d loss / d xy (P,2)."""
+    C, h, w = img.shape; dt = img.dtype.type
+    fx = (xy[:, 0] + dt(1)) * dt(0.5) * dt(w - 1); fy = (xy[:, 1] + dt(1)) * dt(0.5) * dt(h - 1)
+    x0 = np.floor(fx); y0 = np.floor(fy)
+    lx = fx - x0; ly = fy - y0
+    x0 = x0.astype(np.int64); y0 = y0.astype(np.int64)
+    def tap(yy, xx):
+        ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+        v = img[:, np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)].T            # (P,C)
+        return np.where(ok[:, None], v, dt(0))
+    v00, v01, v10, v11 = tap(y0, x0), tap(y0, x0 + 1), tap(y0 + 1, x0), tap(y0 + 1, x0 + 1)
+    lx_, ly_ = lx[:, None], ly[:, None]
+    out = v00 * (1 - lx_) * (1 - ly_) + v01 * lx_ * (1 - ly_) + v10 * (1 - lx_) * ly_ + v11 * lx_ * ly_
+    if g_out is None:
+        return out
+    d_fx = ((v01 - v00) * (1 - ly_) + (v11 - v10) * ly_)
+    d_fy = ((v10 - v00) * (1 - lx_) + (v11 - v01) * lx_)
+    g_xy = np.stack([(g_out * d_fx).sum(1) * dt(0.5) * dt(w - 1), (g_out * d_fy).sum(1) * dt(0.5) * dt(h - 1)], -1)
+    return out, g_xy
+
+
+def ref_stage(img, ref_img, d_in_raw, d_ref_raw, c2w, c2w_ref, scale_in, shift_in, scale_ref, shift_ref, is_last, kx, ky,
+              w_pc=1.0, w_rgb_s=1.0, cfg=REF_CFG):
+    """Forward and adjoint of the reference-image stage (training.py:280-365) with the defaults `detach_ref_img: True`,
+    `shift_first: False`, `match_method: dense`, `with_ssim: False`.
+
+    img, ref_img (3,H,W); d_in_raw, d_ref_raw (h_d,w_d) raw DPT maps; c2w, c2w_ref (4,4); scale/shift: effective
+    distortion of the two views; is_last: current view is the last camera (roles of the views swap, training.py:296-313).
+    Returns (dict(loss_pc, loss_rgb_s), dict(c2w (4,4), scale, shift) = gradients of w_pc*loss_pc + w_rgb_s*loss_rgb_s w.r.t.
+    the CURRENT view's pose matrix and effective distortion; the reference view is detached)."""
+    dt = img.dtype.type
+    nl = dt(cfg["nearest_limit"])
+    hd, wd = d_in_raw.shape
+    res = (int(hd / cfg["pc_ratio"]), int(wd / cfg["pc_ratio"]))
+    P = res[0] * res[1]
+    # pixel grid of the low-resolution maps (arange_pixels, common.py:13-39) and the two depth maps
+    ys, xs = np.meshgrid(np.arange(res[0]), np.arange(res[1]), indexing="ij")
+    px = (dt(2) * xs.reshape(-1).astype(img.dtype) / dt(res[1] - 1) - dt(1)); py = (dt(2) * ys.reshape(-1).astype(img.dtype) / dt(res[0] - 1) - dt(1))
+    raw_in, _, _ = nearest_resize(d_in_raw, res); raw_ref, _, _ = nearest_resize(d_ref_raw, res)
+    raw_in = raw_in.reshape(-1).astype(img.dtype); raw_ref = raw_ref.reshape(-1).astype(img.dtype)
+    din = raw_in * dt(scale_in) + dt(shift_in); dref = raw_ref * dt(scale_ref) + dt(shift_ref)     # training.py:241-245, 283-287
+    live_in = din >= nl                                                                           # d[d < nl] = nl (training.py:320-321)
+    din_c = np.where(live_in, din, nl); dref_c = np.where(dref >= nl, dref, nl)
+    bp = lambda d: np.stack([px * d / dt(kx), py * d / dt(ky), -d], -1)                           # transform_to_world, identity pose
+    if not is_last:
+        d1, d2 = din_c, dref_c; img1, img2 = img, ref_img
+        M = np.linalg.inv(c2w_ref) @ c2w                                                          # ref_Rt @ inverse(world_mat)
+        s2 = dt(scale_ref)
+    else:
+        d1, d2 = dref_c, din_c; img1, img2 = ref_img, img
+        inv_c2w = np.linalg.inv(c2w)
+        M = inv_c2w @ c2w_ref                                                                     # world_mat @ inverse(ref_Rt)
+        s2 = dt(scale_in)
+    M = M.astype(img.dtype)
+    R, t = M[:3, :3], M[:3, 3]
+    pc1, pc2 = bp(d1), bp(d2)
+    g_pc1 = np.zeros_like(pc1); g_pc2 = np.zeros_like(pc2); gR = np.zeros((3, 3), img.dtype); gt = np.zeros(3, img.dtype)
+    g_s2 = dt(0)
+    losses = dict(loss_pc=dt(0), loss_rgb_s=dt(0))
+    # ---- warped-RGB term (training.py:325-341, losses.py:150-157,77-85) ----
+    if w_rgb_s != 0.0:
+        i1, i2 = bilinear_resize(img1, res), bilinear_resize(img2, res)
+        rgb1 = grid_sample_bilinear(i1, np.stack([px, py], -1))
+        Xr = pc1 @ R.T + t
+        bad = (-Xr[:, 2] < nl)
+        Xr_c = np.where(bad[:, None], nl, Xr)                                                     # behind-camera fix-up (:334-335)
+        z = -Xr_c[:, 2]
+        xy = np.stack([dt(kx) * Xr_c[:, 0] / z, dt(ky) * Xr_c[:, 1] / z], -1)                     # project_to_cam (common.py:436-457)
+        valid = np.abs(xy).max(-1) <= 1
+        nv = int(valid.sum()) * 3
+        diff = rgb1 - grid_sample_bilinear(i2, xy)
+        ad = np.clip(np.abs(diff), 0, 1)
+        losses["loss_rgb_s"] = ad[valid].sum() / dt(max(nv, 1)) if nv > 0 else dt(0)
+        if nv > 0:
+            g_proj = np.where(valid[:, None] & (np.abs(diff) < 1), -np.sign(diff), dt(0)) * dt(w_rgb_s) / dt(nv)
+            _, g_xy = grid_sample_bilinear(i2, xy, g_proj)
+            gX = np.stack([g_xy[:, 0] * dt(kx) / z, g_xy[:, 1] * dt(ky) / z,
+                           (g_xy[:, 0] * dt(kx) * Xr_c[:, 0] + g_xy[:, 1] * dt(ky) * Xr_c[:, 1]) / (z * z)], -1)
+            gX = np.where(bad[:, None], dt(0), gX)
+            gR += gX.T @ pc1; gt += gX.sum(0)
+            if not cfg["detach_rgbs_scale"]:
+                g_pc1 += gX @ R
+    # ---- point-cloud term (training.py:355-362, losses.py:114-148) ----
+    if w_pc != 0.0:
+        X = pc1 @ R.T + t; Y = pc2
+        if cfg["scale_pcs"]:
+            Xs, Ys = X / s2, Y / s2
+        else:
+            Xs, Ys = X, Y
+        l, gXs, gYs, _, _ = chamfer(Xs, Ys)
+        losses["loss_pc"] = l
+        gXs = gXs * dt(w_pc); gYs = gYs * dt(w_pc)
+        if cfg["scale_pcs"]:
+            g_s2 = -((gXs * Xs).sum() + (gYs * Ys).sum()) / s2
+            gX, gY = gXs / s2, gYs / s2
+        else:
+            gX, gY = gXs, gYs
+        gR += gX.T @ pc1; gt += gX.sum(0); g_pc1 += gX @ R; g_pc2 += gY
+    # ---- back to the current view's pose and distortion ----
+    gM = np.zeros((4, 4), img.dtype); gM[:3, :3] = gR; gM[:3, 3] = gt
+    if not is_last:
+        g_c2w = np.linalg.inv(c2w_ref).T.astype(img.dtype) @ gM
+        g_d = g_pc1[:, 0] * px / dt(kx) + g_pc1[:, 1] * py / dt(ky) - g_pc1[:, 2]                 # d1 = current view's depth
+        g_scale_extra = dt(0)                                                                     # scale2 = detached reference scale
+    else:
+        g_inv = gM @ c2w_ref.T.astype(img.dtype)
+        g_c2w = -(inv_c2w.T.astype(img.dtype) @ g_inv @ inv_c2w.T.astype(img.dtype))
+        g_d = g_pc2[:, 0] * px / dt(kx) + g_pc2[:, 1] * py / dt(ky) - g_pc2[:, 2]                 # d2 = current view's depth
+        g_scale_extra = g_s2                                                                      # scale2 = current view's scale
+    g_d = np.where(live_in, g_d, dt(0))
+    grads = dict(c2w=g_c2w, scale=(g_d * raw_in).sum() + g_scale_extra, shift=g_d.sum())
+    return losses, grads
+
+
+# ----------------------------------------------------------------------------
 # Adam (torch.optim.Adam defaults as used at train.py:58,99,117)
 # ----------------------------------------------------------------------------
 def adam_step(p, g, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
@@ -494,9 +638,22 @@ def adam_step(p, g, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
 # ----------------------------------------------------------------------------
 # One optimisation step (model/training.py:67-97 + compute_loss:197-378, render terms)
 # ----------------------------------------------------------------------------
+def _distortion(state, cam_id, dt, cfg):
+    """Learn_Distortion.forward (distortions.py:19-27): (scale_eff, shift, scale is a live parameter)"""
+    V = state["r"].shape[0]
+    scale = state["scales"][cam_id, 0]; shift = state["shifts"][cam_id, 0]
+    scale_eff, live = scale, True
+    if scale < 0.01:
+        scale_eff, live = dt(0.01), False
+    if cfg.get("fix_scaleN", True) and cam_id == V - 1:
+        scale_eff, live = dt(1.0), False
+    return scale_eff, shift, live
+
+
 def train_step(state, img, dpt, ray_idx, noise, cam_id, kx, ky, cfg, w_rgb=1.0, w_depth=0.04,
-               rgb_loss_type="l1", lrs=(1e-3, 5e-4, 5e-4), apply_update=True):
-    """Trainer.train_step with pc/rgb_s weights = 0 (render + rgb + depth losses).
+               rgb_loss_type="l1", lrs=(1e-3, 5e-4, 5e-4), apply_update=True, ref=None):
+    """Trainer.train_step: render + rgb + depth losses, and with ref = dict(img (3,H,W), dpt (h_d,w_d), idx, w_pc, w_rgb_s)
+    also the reference-image stage (point-cloud + warped-RGB terms, training.py:280-365).
     state: dict(P, r (V,3), t (V,3), scales (V,1), shifts (V,1), adam={...}, step).
     img (3,H,W); dpt (h_d,w_d).  Returns loss dict + grads."""
     P = state["P"]; dt = img.dtype.type
@@ -519,10 +676,22 @@ def train_step(state, img, dpt, ray_idx, noise, cam_id, kx, ky, cfg, w_rgb=1.0, 
     ld, g_rgb, g_dp, g_dg = loss_rgb_depth(out["rgb"], rgb_gt, out["depth_pred_full"], out["depth_gt_full"],
                                            out["mask"], w_rgb, w_depth, rgb_loss_type)
     gr = render_backward(P, cache, g_rgb, g_dp, g_dg)
-    g_r, g_t = make_c2w_bwd(r, t, None if init is None else init[cam_id], gr["c2w"])
+    g_c2w = gr["c2w"]
     g_scale = (gr["depth"] * raw).sum() if scale_live else dt(0)
     g_shift = gr["depth"].sum()
-    grads = dict(P=gr["params"], r=g_r, t=g_t, scale=g_scale, shift=g_shift, c2w=gr["c2w"])
+    if ref is not None:
+        ri = int(ref["idx"])
+        c2w_ref = make_c2w(state["r"][ri], state["t"][ri], None if init is None else init[ri])
+        s_ref, h_ref, _ = _distortion(state, ri, dt, cfg)
+        w_pc, w_rgb_s = ref.get("w_pc", 1.0), ref.get("w_rgb_s", 1.0)
+        rl, rg = ref_stage(img, ref["img"], dpt, ref["dpt"], c2w, c2w_ref, scale_eff, shift, s_ref, h_ref, cam_id == V - 1, kx, ky,
+                           w_pc=w_pc, w_rgb_s=w_rgb_s)
+        ld["loss_pc"] = rl["loss_pc"]; ld["loss_rgb_s"] = rl["loss_rgb_s"]
+        ld["loss"] = ld["loss"] + dt(w_pc) * rl["loss_pc"] + dt(w_rgb_s) * rl["loss_rgb_s"]
+        g_c2w = g_c2w + rg["c2w"]
+        g_scale = g_scale + (rg["scale"] if scale_live else dt(0)); g_shift = g_shift + rg["shift"]
+    g_r, g_t = make_c2w_bwd(r, t, None if init is None else init[cam_id], g_c2w)
+    grads = dict(P=gr["params"], r=g_r, t=g_t, scale=g_scale, shift=g_shift, c2w=g_c2w)
     if apply_update:
         state["step"] = state.get("step", 0) + 1
         ad = state.setdefault("adam", {})

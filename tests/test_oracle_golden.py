@@ -149,3 +149,41 @@ def test_chamfer_dense():
     assert relmax(gX, g["gX"]) < 1e-5 and relmax(gY, g["gY"]) < 1e-5
     assert ixy[7] == 5 and not np.any(ixy == 11)          # the coincident pair; the duplicate at 11 never wins against index 3
     assert np.isfinite(gX).all() and np.isfinite(gY).all()
+
+
+@pytest.mark.parametrize("name", ["train_full_losses", "train_full_lastview"])
+def test_train_step_full_losses(name):
+    """oracle.train_step with the reference-image stage (point-cloud chamfer + warped-RGB terms, training.py:280-365) vs the
+    reference Trainer.train_step with the default loss set; `train_full_lastview` has the current view as the LAST camera
+    (the two views swap roles, the scale of the last view is the fixed constant 1)."""
+    g = load_golden(name)
+    idx = int(g["idx"])
+
+    def run(dtype):
+        cfg = dict(O.DEFAULT_CFG); cfg["num_points"] = int(g["S"])
+        state = dict(P={k: v.astype(dtype) for k, v in O.init_params(seed=int(g["seed"])).items()},
+                     r=g["r0"].astype(dtype).copy(), t=g["t0"].astype(dtype).copy(),
+                     scales=g["scales0"].astype(dtype).copy(), shifts=g["shifts0"].astype(dtype).copy())
+        hist = []
+        for it in range(int(g["steps"])):
+            ref = dict(img=g["ref"].astype(dtype), dpt=g["rdpt"].astype(dtype), idx=int(g["ref_idx"]), w_pc=1.0, w_rgb_s=1.0)
+            hist.append(O.train_step(state, g["img"].astype(dtype), g["dpt"].astype(dtype), g["ray_idx_%d" % it], g["noise_%d" % it].astype(dtype),
+                                     idx, dtype(g["kx"]), dtype(g["ky"]), cfg, w_rgb=1.0, w_depth=0.04, rgb_loss_type="l1", ref=ref)[:2])
+        return state, hist
+    st32, h32 = run(np.float32)
+    st64, h64 = run(np.float64)
+    for it in range(int(g["steps"])):
+        ld, gr = h32[it]; _, gr64 = h64[it]
+        for k in ("loss", "loss_rgb", "loss_depth", "loss_pc", "loss_rgb_s"):
+            ref = float(np.ravel(g["loss_%d.%s" % (it, k)])[0])
+            assert abs(float(ld[k]) - ref) / abs(ref) < 5e-5, (it, k, float(ld[k]), ref)
+        for nm, key in (("r", "grad_r_%d"), ("t", "grad_t_%d")):
+            ref = g[key % it][idx]
+            env = relmax(gr64[nm], ref)
+            assert relmax(gr[nm], ref) < max(2e-4, 3 * env), (it, nm, relmax(gr[nm], ref), env)
+        ref_ss = np.array([g["grad_scales_%d" % it][idx, 0], g["grad_shifts_%d" % it][idx, 0]])
+        env = relmax(np.array([gr64["scale"], gr64["shift"]]), ref_ss)
+        assert relmax(np.array([gr["scale"], gr["shift"]]), ref_ss) < max(2e-4, 3 * env), (it, gr["scale"], gr["shift"], ref_ss)
+    for key in ("r", "t", "scales", "shifts"):
+        upd_ref = g[key + "_end"] - g[key + "0"]
+        assert relmax(st32[key] - g[key + "0"], upd_ref) < 2e-3, key
