@@ -145,6 +145,24 @@ int nnb_loss_rgb_depth(const float* rgb, const float* rgb_gt, const float* img, 
 int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, int32_t* idx_xy, int32_t* idx_yx,
                 float* loss, float weight, float* gX, float* gY, void* stream);
 
+/* Reference-image stage of Trainer.compute_loss (model/training.py:280-365): point-cloud (dense chamfer) + warped-RGB terms
+ * between the current view and one detached reference view, forward AND adjoint in one call.  EXPERIMENTAL (round 1): the
+ * per-point arithmetic is checked on the CPU against the oracle, the kernels have not run on hardware yet.
+ *   img_* (3,H,W) planar fp32; dpt_* (h_d,w_d) raw DPT maps; c2w_* (4,4) row-major; dist_* = {effective scale, shift}
+ *   (Learn_Distortion.forward) -- all device pointers.  flags: 1 = scale_pcs, 2 = detach_rgbs_scale.
+ *   losses[2] = {loss_pc, loss_rgb_s}; g_c2w[16] / g_dist[2] ACCUMULATE d(w_pc*loss_pc + w_rgb_s*loss_rgb_s) / d(c2w_cur, dist_cur). */
+typedef struct {
+  const float* img_cur; const float* img_ref; const float* dpt_cur; const float* dpt_ref;
+  const float* c2w_cur; const float* c2w_ref; const float* dist_cur; const float* dist_ref;
+  int32_t H, W, h_d, w_d, pc_ratio, is_last;
+  uint32_t flags;
+  float kx, ky, nearest_limit, w_pc, w_rgb_s;
+  float* losses; float* g_c2w; float* g_dist;
+  void* workspace; size_t workspace_bytes;       /* >= nnb_refstage_workspace_bytes(h_d, w_d, pc_ratio) */
+} nnb_refstage_args;
+size_t nnb_refstage_workspace_bytes(int32_t h_d, int32_t w_d, int32_t pc_ratio);
+int nnb_refstage(const nnb_refstage_args* args, void* stream);
+
 /* torch.optim.Adam step (train.py:58,99,117 defaults) over one flat buffer. step_count is the
  * 1-based step; lr/betas/eps as torch. */
 int nnb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,

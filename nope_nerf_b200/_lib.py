@@ -30,6 +30,13 @@ class RenderBwdArgs(C.Structure):
                 ("g_weights", _f), ("g_c2w", _f), ("g_cam", _f), ("g_depth", _f), ("g_scale_shift", _f)]
 
 
+class RefStageArgs(C.Structure):
+    _fields_ = [("img_cur", _f), ("img_ref", _f), ("dpt_cur", _f), ("dpt_ref", _f), ("c2w_cur", _f), ("c2w_ref", _f), ("dist_cur", _f), ("dist_ref", _f),
+                ("H", C.c_int32), ("W", C.c_int32), ("h_d", C.c_int32), ("w_d", C.c_int32), ("pc_ratio", C.c_int32), ("is_last", C.c_int32),
+                ("flags", C.c_uint32), ("kx", C.c_float), ("ky", C.c_float), ("nearest_limit", C.c_float), ("w_pc", C.c_float), ("w_rgb_s", C.c_float),
+                ("losses", _f), ("g_c2w", _f), ("g_dist", _f), ("workspace", _f), ("workspace_bytes", C.c_size_t)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
@@ -60,9 +67,9 @@ def _load():
     lib.nnb_sample_pixels.argtypes = [_f, C.c_int32, C.c_int32, _f, C.c_void_p]
     lib.nnb_loss_rgb_depth_indirect.argtypes = [_f, _f, _f, C.c_int32, _f, _f, _f, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, _f, _f,
                                                 _f, _f, C.c_void_p]
-    for name in ("nnb_refstage_fwd", "nnb_refstage_bwd"):
-        if hasattr(lib, name):
-            getattr(lib, name).restype = C.c_int
+    lib.nnb_refstage_workspace_bytes.restype = C.c_size_t
+    lib.nnb_refstage_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.nnb_refstage.argtypes = [C.POINTER(RefStageArgs), C.c_void_p]
     return lib
 
 

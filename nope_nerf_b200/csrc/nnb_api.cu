@@ -27,6 +27,8 @@ cudaError_t launch_loss(const float*, const float*, const float*, const float* c
                         int, float, float, int, float, float*, float*, float*, float*, cudaStream_t);
 cudaError_t launch_chamfer(const float*, int, const float*, int, int*, int*, float*, float, float*, float*, cudaStream_t);
 cudaError_t launch_adam(float*, const float*, float*, float*, int64_t, int, float, float, float, float, cudaStream_t);
+size_t refstage_workspace_bytes(int hd, int wd, int ratio);
+cudaError_t launch_refstage(const nnb_refstage_args& a, cudaStream_t st);
 
 // optional profiling hook (bench.py): CUDA events recorded between the kernels of one call
 static cudaEvent_t* g_prof_events = nullptr;
@@ -216,6 +218,22 @@ int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, int32_t* i
     return fail(-3, "nnb_chamfer: bad arguments");
   cudaError_t e = launch_chamfer(X, P, Y, Q, ixy, iyx, loss, weight, gX, gY, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_chamfer");
+}
+
+size_t nnb_refstage_workspace_bytes(int32_t h_d, int32_t w_d, int32_t pc_ratio) {
+  if (h_d <= 0 || w_d <= 0 || pc_ratio <= 0 || h_d / pc_ratio < 2 || w_d / pc_ratio < 2) return 0;
+  return refstage_workspace_bytes(h_d, w_d, pc_ratio);
+}
+
+int nnb_refstage(const nnb_refstage_args* a, void* stream) {
+  if (!a) return fail(-1, "null args");
+  if (!a->img_cur || !a->img_ref || !a->dpt_cur || !a->dpt_ref || !a->c2w_cur || !a->c2w_ref || !a->dist_cur || !a->dist_ref || !a->losses)
+    return fail(-3, "nnb_refstage: null pointer");
+  if (a->H < 2 || a->W < 2 || a->pc_ratio <= 0 || a->h_d / a->pc_ratio < 2 || a->w_d / a->pc_ratio < 2)
+    return fail(-2, "nnb_refstage: bad sizes");
+  if (!a->workspace || a->workspace_bytes < refstage_workspace_bytes(a->h_d, a->w_d, a->pc_ratio)) return fail(-4, "nnb_refstage: workspace too small");
+  cudaError_t e = launch_refstage(*a, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_refstage");
 }
 
 int nnb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float b1, float b2, float eps,

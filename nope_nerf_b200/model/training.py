@@ -364,6 +364,8 @@ class Trainer(object):
         # 'randperm' = the reference's torch.randperm(H*W)[:N] (identical RNG stream in eager mode); 'hash' = nnb_sample_pixels;
         # 'auto' = randperm when running eagerly, hash inside the CUDA graph (whose RNG stream differs from eager anyway)
         self.pixel_sampler = kwargs.get('pixel_sampler', 'auto')
+        # EXPERIMENTAL (round 1): the reference-image stage as fused CUDA kernels (nnb_refstage) instead of the torch statement
+        self.native_ref_stage = bool(kwargs.get('native_ref_stage', False))
 
     # ------------------------------------------------------------------------------------
     def _grad_buffer(self):
@@ -623,6 +625,24 @@ class Trainer(object):
         pose = self.pose_param_net
         num_cams = pose.num_cams
         nl = self.nearest_limit
+        if self.native_ref_stage:
+            if self.shift_first or not self.detach_ref_img:
+                raise NotImplementedError("native_ref_stage covers the default shift_first=False, detach_ref_img=True")
+            if self.distortion_net is not None:
+                s_ref, h_ref = self.distortion_net(ref_idx)
+            else:
+                s_ref = torch.ones(1, device=device); h_ref = torch.zeros(1, device=device)
+            dist_cur = torch.stack([scale_input.reshape(()), shift_input.reshape(())])
+            dist_ref = torch.stack([s_ref.reshape(()), h_ref.reshape(())]).detach()
+            cm = camera_mat.reshape(4, 4)
+            total, losses = ops.refstage(pose(img_idx), dist_cur, pose(ref_idx).detach(), dist_ref, img[0], ref_img[0], depth_input[0, 0],
+                                         depth_ref[0, 0], img_idx == num_cams - 1, float(cm[0, 0]), float(cm[1, 1]), nearest_limit=nl,
+                                         pc_ratio=self.pc_ratio, scale_pcs=self.scale_pcs, detach_rgbs_scale=self.detach_rgbs_scale,
+                                         w_pc=weights['pc_weight'], w_rgb_s=weights['rgb_s_weight'])
+            terms = {}
+            if weights['pc_weight'] != 0.0: terms['loss_pc'] = losses[0]
+            if weights['rgb_s_weight'] != 0.0: terms['loss_rgb_s'] = losses[1]
+            return total, terms
         _, _, h_depth, w_depth = depth_input.shape
         c2w = pose(img_idx)                                         # differentiable (nnb_pose_fwd/bwd)
         if self.shift_first: d_in = (depth_input + shift_input) * scale_input       # training.py:241-245

@@ -265,6 +265,46 @@ def chamfer(X, Y):
     return _ChamferFn.apply(X, Y)
 
 
+class _RefStageFn(torch.autograd.Function):
+    """w_pc * loss_pc + w_rgb_s * loss_rgb_s of the reference-image stage (model/training.py:280-365) as a function of the current
+    view's pose matrix and effective distortion {scale, shift}; forward and adjoint come out of ONE library call (nnb_refstage)."""
+
+    @staticmethod
+    def forward(ctx, c2w_cur, dist_cur, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, kx, ky, nearest_limit, pc_ratio,
+                scale_pcs, detach_rgbs_scale, w_pc, w_rgb_s):
+        dev = c2w_cur.device
+        c2w_cur = _f32c(c2w_cur.detach()); dist_cur = _f32c(dist_cur.detach()); c2w_ref = _f32c(c2w_ref.detach()); dist_ref = _f32c(dist_ref.detach())
+        img_cur = _f32c(img_cur); img_ref = _f32c(img_ref); dpt_cur = _f32c(dpt_cur); dpt_ref = _f32c(dpt_ref)
+        H, W = img_cur.shape[-2:]; hd, wd = dpt_cur.shape[-2:]
+        nbytes = L.lib.nnb_refstage_workspace_bytes(int(hd), int(wd), int(pc_ratio))
+        if nbytes == 0:
+            raise ValueError("reference-image stage: DPT map %dx%d too small for pc_ratio %d" % (hd, wd, pc_ratio))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        losses = torch.zeros(2, device=dev); g_c2w = torch.zeros(4, 4, device=dev); g_dist = torch.zeros(2, device=dev)
+        a = L.RefStageArgs(L.ptr(img_cur), L.ptr(img_ref), L.ptr(dpt_cur), L.ptr(dpt_ref), L.ptr(c2w_cur), L.ptr(c2w_ref), L.ptr(dist_cur),
+                           L.ptr(dist_ref), int(H), int(W), int(hd), int(wd), int(pc_ratio), int(bool(is_last)),
+                           (1 if scale_pcs else 0) | (2 if detach_rgbs_scale else 0), float(kx), float(ky), float(nearest_limit), float(w_pc),
+                           float(w_rgb_s), L.ptr(losses), L.ptr(g_c2w), L.ptr(g_dist), L.ptr(ws), nbytes)
+        L.check(L.lib.nnb_refstage(a, _stream()), "nnb_refstage")
+        ctx.save_for_backward(g_c2w, g_dist)
+        ctx.mark_non_differentiable(losses)
+        return float(w_pc) * losses[0] + float(w_rgb_s) * losses[1], losses
+
+    @staticmethod
+    def backward(ctx, g, _g_losses):
+        g_c2w, g_dist = ctx.saved_tensors
+        return (g_c2w * g if ctx.needs_input_grad[0] else None, g_dist * g if ctx.needs_input_grad[1] else None) + (None,) * 15
+
+
+def refstage(c2w_cur, dist_cur, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, kx, ky, nearest_limit=0.01, pc_ratio=4,
+             scale_pcs=True, detach_rgbs_scale=False, w_pc=1.0, w_rgb_s=1.0):
+    """(total, losses[2] = {loss_pc, loss_rgb_s}); total is differentiable w.r.t. c2w_cur (4,4) and dist_cur = [scale_eff, shift].
+    EXPERIMENTAL in round 1 (see include/nope_nerf_b200.h)."""
+    _need_cuda(c2w_cur, "c2w_cur")
+    return _RefStageFn.apply(c2w_cur, dist_cur, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, kx, ky, nearest_limit, pc_ratio,
+                             scale_pcs, detach_rgbs_scale, w_pc, w_rgb_s)
+
+
 def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     L.check(L.lib.nnb_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), int(step), float(lr), beta1, beta2, eps,
                                 _stream()), "nnb_adam_step")

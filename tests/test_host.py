@@ -182,3 +182,51 @@ def test_resident_dataset_views_and_reference_frames():
     assert sorted(seen) == list(range(V))
     with pytest.raises(ValueError):
         ResidentDataset(imgs[:, :2], dpts, K, device="cpu")
+
+
+def _ref_stage_case(name, detach=False, scale_pcs=True):
+    """inputs of oracle.ref_stage / nnb_refstage taken from a full-loss golden"""
+    from _util import load_golden
+    g = load_golden(name)
+    idx, ri, V = int(g["idx"]), int(g["ref_idx"]), int(g["V"])
+    state = dict(r=g["r0"], t=g["t0"], scales=g["scales0"], shifts=g["shifts0"])
+    f = np.float32
+    c2w = O.make_c2w(g["r0"][idx], g["t0"][idx]).astype(f); c2wr = O.make_c2w(g["r0"][ri], g["t0"][ri]).astype(f)
+    s_c, h_c, _ = O._distortion(state, idx, f, {}); s_r, h_r, _ = O._distortion(state, ri, f, {})
+    cfg = dict(O.REF_CFG); cfg["detach_rgbs_scale"] = detach; cfg["scale_pcs"] = scale_pcs
+    return dict(g=g, c2w=c2w, c2wr=c2wr, dist=(float(s_c), float(h_c)), distr=(float(s_r), float(h_r)), is_last=(idx == V - 1),
+                kx=float(g["kx"]), ky=float(g["ky"]), cfg=cfg)
+
+
+@pytest.mark.parametrize("name", ["train_full_losses", "train_full_lastview"])
+@pytest.mark.parametrize("detach,scale_pcs", [(False, True), (True, True), (False, False)])
+def test_refstage_device_math_on_host(name, detach, scale_pcs, tmp_path):
+    """nope_nerf_b200/csrc/nnb_refstage.cuh holds the per-point arithmetic of the reference-image stage as __host__ __device__
+    functions; tools/refstage_host_check.cu runs exactly those functions on the CPU (plus a brute-force chamfer with the
+    kernels' arithmetic).  Compared here with oracle.ref_stage, which is pinned to the reference's full-loss train steps."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = os.path.join(ROOT, "nope_nerf_b200", "build", "refstage_host_check")
+    src = os.path.join(ROOT, "tools", "refstage_host_check.cu"); hdr = os.path.join(ROOT, "nope_nerf_b200", "csrc", "nnb_refstage.cuh")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call([nvcc, "-O1", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src])
+    c = _ref_stage_case(name, detach, scale_pcs)
+    g = c["g"]
+    H, W = g["img"].shape[1:]; hd, wd = g["dpt"].shape
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as fo:
+        np.array([H, W, hd, wd, 4, int(c["is_last"]), int(scale_pcs), int(detach)], np.int32).tofile(fo)
+        np.array([c["kx"], c["ky"], 0.01, c["dist"][0], c["dist"][1], c["distr"][0], c["distr"][1], 1.0, 1.0], np.float32).tofile(fo)
+        for arr in (c["c2w"], c["c2wr"], g["img"], g["ref"], g["dpt"], g["rdpt"]):
+            np.ascontiguousarray(arr, np.float32).tofile(fo)
+    subprocess.check_call([exe, fin, fout])
+    o = np.fromfile(fout, np.float32)
+    l, gr = O.ref_stage(g["img"], g["ref"], g["dpt"], g["rdpt"], c["c2w"], c["c2wr"], c["dist"][0], c["dist"][1], c["distr"][0], c["distr"][1],
+                        c["is_last"], np.float32(c["kx"]), np.float32(c["ky"]), cfg=c["cfg"])
+    assert abs(o[0] - l["loss_pc"]) < 2e-6 * abs(l["loss_pc"]) and abs(o[1] - l["loss_rgb_s"]) < 2e-6 * abs(l["loss_rgb_s"])
+    from _util import relmax
+    assert relmax(o[2:18].reshape(4, 4)[:3], gr["c2w"][:3]) < 2e-5
+    assert abs(o[18] - gr["scale"]) < 2e-5 * max(abs(gr["scale"]), 1.0) and abs(o[19] - gr["shift"]) < 2e-5 * max(abs(gr["shift"]), 1.0)
