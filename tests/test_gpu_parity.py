@@ -512,3 +512,40 @@ def test_native_ref_stage_vs_oracle(name):
              g_dist=relmax(dist.grad.cpu().numpy(), np.array([gr["scale"], gr["shift"]])))
     _report("native_ref_stage/%s" % name, **e)
     assert e["loss_pc"] < 1e-5 and e["loss_rgb_s"] < 1e-5 and e["g_c2w"] < 1e-4 and e["g_dist"] < 1e-4, e
+
+
+@pytest.mark.parametrize("N,S", [(5, 32), (3, 64), (7, 32), (130, 32)])
+def test_ragged_last_tile_tc_vs_simt(N, S):
+    """N*S not a multiple of the 128-sample tile: the tcgen05 engine pads the last tile with clamped rows whose cotangents are
+    zero; outputs and gradients must agree with the exact-fp32 engine.  Every size the suite ran on hardware so far is a
+    multiple of 128 samples, so this case runs with NNB_EXPERIMENTAL=1 until it has passed once."""
+    if os.environ.get("NNB_EXPERIMENTAL", "0") != "1":
+        pytest.skip("set NNB_EXPERIMENTAL=1 (size class not yet run on hardware)")
+    from nope_nerf_b200 import ops, _lib as L
+    if len(engines()) < 2:
+        pytest.skip("needs both engines")
+    H, W = 40, 56
+    gen = torch.Generator(device="cuda").manual_seed(N * 1000 + S)
+    flat = cuda(O.flatten_params(O.init_params(seed=5)))
+    r = torch.randn(3, 3, device="cuda", generator=gen) * 0.05; t = torch.randn(3, 3, device="cuda", generator=gen) * 0.05
+    c2w = torch.empty(4, 4, device="cuda"); ops.pose_fwd_raw(r, t, None, 1, c2w)
+    cam = torch.diag(torch.tensor([1.2, -1.6, -1.0, 1.0])).cuda()
+    ray_idx = torch.randperm(H * W, device="cuda", generator=gen)[:N]
+    dpt = torch.rand(20, 28, device="cuda", generator=gen) * 6.6 + 0.6
+    noise = torch.rand(N, S, device="cuda", generator=gen)
+    flags = ops.flags_from_cfg(dict(O.DEFAULT_CFG), "softplus")
+    g_rgb = torch.randn(N, 3, device="cuda", generator=gen) / N; g_dp = torch.randn(N, device="cuda", generator=gen) / N
+    res = {}
+    for name, engine in engines():
+        call = ops.RenderCall(flat, c2w, cam, N=N, S=S, flags=flags, engine=engine, near=0.01, far=10.0, ray_idx=ray_idx, depth_map=dpt,
+                              noise=noise, H=H, W=W, stash=True)
+        g_w = torch.zeros(L.NUM_PARAMS, device="cuda"); g_c = torch.zeros(4, 4, device="cuda"); g_ss = torch.zeros(2, device="cuda")
+        rgb, dp = call.rgb.clone(), call.depth_pred.clone()
+        call.backward(g_rgb, g_dp, None, g_w, g_c, None, None, g_ss)
+        torch.cuda.synchronize()
+        res[name] = (rgb, dp, g_w, g_c, g_ss)
+    a, b = res["simt"], res["tc"]
+    rel = lambda x, y: ((x - y).abs().max() / x.abs().max().clamp_min(1e-30)).item()
+    e = dict(rgb=rel(a[0], b[0]), dp=rel(a[1], b[1]), gw=rel(a[2], b[2]), gc=rel(a[3], b[3]), gss=rel(a[4], b[4]))
+    _report("ragged/%dx%d" % (N, S), **e)
+    assert e["rgb"] < 1e-4 and e["dp"] < 1e-4 and e["gw"] < 2e-3 and e["gc"] < 2e-3 and e["gss"] < 2e-3, e
