@@ -127,10 +127,12 @@ int nnb_counter_incr(int32_t* counters, int32_t n, void* stream);
 /* N distinct pixel ids uniform in [0,HW) from 2N uniforms u in [0,1): same distribution as torch.randperm(HW)[:N]
  * (model/training.py:257) without sorting HW keys.  0 < N <= min(HW/2, 8192). */
 int nnb_sample_pixels(const float* u2n, int32_t HW, int32_t N, int64_t* out, void* stream);
+/* w_dev (optional): device {w_rgb, w_depth} overriding the host weights -- the annealed weights of training.py:208-217 change per
+ * epoch without re-capturing the graph */
 int nnb_loss_rgb_depth_indirect(const float* rgb, const float* const* img_pp /* device pointer to the frame pointer */, const int64_t* ray_idx,
                                 int32_t HW, const float* depth_pred, const float* depth_gt, const uint8_t* mask, int32_t N, float w_rgb,
                                 float w_depth, int32_t rgb_l2, float grad_scale, float* out_losses, float* g_rgb, float* g_depth_pred,
-                                float* g_depth_gt, void* stream);
+                                float* g_depth_gt, const float* w_dev, void* stream);
 
 /* Loss.forward photometric + depth-L1 terms (model/losses.py:27-32,59-61,192,196-202) fused with
  * the cotangent seeds of nnb_render_bwd.  rgb_gt is either explicit [N,3] or gathered from a planar
@@ -140,18 +142,23 @@ int nnb_loss_rgb_depth(const float* rgb, const float* rgb_gt, const float* img, 
                        float w_rgb, float w_depth, int32_t rgb_l2, float grad_scale, float* out_losses /*[4]*/,
                        float* g_rgb, float* g_depth_pred, float* g_depth_gt, void* stream);
 
-/* Loss.get_pc_loss 'dense' (model/losses.py:114-148): symmetric mean nearest-neighbour distance.
- * X [P,3], Y [Q,3]; idx_xy [P], idx_yx [Q] int32 scratch; loss [1] (+=); optional adjoints (+=). */
-int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, int32_t* idx_xy, int32_t* idx_yx,
+/* Loss.get_pc_loss 'dense' (model/losses.py:114-148): symmetric mean nearest-neighbour distance (brute force, argmin ties ->
+ * first index like torch.argmin).  X [P,3], Y [Q,3]; keys [P+Q] 64-bit scratch; idx_xy [P], idx_yx [Q] optional int32
+ * nearest-neighbour outputs (both or neither); loss [1] (+=); optional adjoints gX, gY (+=, both or neither). */
+int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, uint64_t* keys, int32_t* idx_xy, int32_t* idx_yx,
                 float* loss, float weight, float* gX, float* gY, void* stream);
 
 /* Reference-image stage of Trainer.compute_loss (model/training.py:280-365): point-cloud (dense chamfer) + warped-RGB terms
- * between the current view and one detached reference view, forward AND adjoint in one call.  EXPERIMENTAL (round 1): the
- * per-point arithmetic is checked on the CPU against the oracle, the kernels have not run on hardware yet.
+ * between the current view and one detached reference view (training.detach_ref_img = True, the default), forward AND adjoint
+ * in one call.
  *   img_* (3,H,W) planar fp32; dpt_* (h_d,w_d) raw DPT maps; c2w_* (4,4) row-major; dist_* = {effective scale, shift}
- *   (Learn_Distortion.forward) -- all device pointers.  flags: 1 = scale_pcs, 2 = detach_rgbs_scale.
- *   losses[2] = {loss_pc, loss_rgb_s}; g_c2w[16] / g_dist[2] ACCUMULATE d(w_pc*loss_pc + w_rgb_s*loss_rgb_s) / d(c2w_cur, dist_cur). */
-typedef struct {
+ *   (Learn_Distortion.forward) -- all device pointers.  flags: 1 = scale_pcs, 2 = detach_rgbs_scale, 4 = shift_first.
+ *   losses[2] = {loss_pc, loss_rgb_s}; g_c2w[16] / g_dist[2] / g_kxy[2] ACCUMULATE grad_scale * d(w_pc*loss_pc + w_rgb_s*loss_rgb_s) /
+ *   d(c2w_cur, dist_cur, (kx, ky)); loss_total (optional) += the weighted sum.
+ * CUDA-graph replay: per-step values may come from device memory instead of the host fields -- img_pp (device array of the two
+ * frame pointers {cur, ref}, replaces img_cur / img_ref), cam (device camera_mat [16]: kx = cam[0], ky = cam[5]), cam_idx_dev +
+ * num_cams (is_last = *cam_idx_dev == num_cams - 1), weights_dev ({w_pc, w_rgb_s}). */
+typedef struct nnb_refstage_args {
   const float* img_cur; const float* img_ref; const float* dpt_cur; const float* dpt_ref;
   const float* c2w_cur; const float* c2w_ref; const float* dist_cur; const float* dist_ref;
   int32_t H, W, h_d, w_d, pc_ratio, is_last;
@@ -159,6 +166,9 @@ typedef struct {
   float kx, ky, nearest_limit, w_pc, w_rgb_s;
   float* losses; float* g_c2w; float* g_dist;
   void* workspace; size_t workspace_bytes;       /* >= nnb_refstage_workspace_bytes(h_d, w_d, pc_ratio) */
+  /* optional (NULL / 0 = unused) */
+  const float* const* img_pp; const float* cam; const int32_t* cam_idx_dev; int32_t num_cams; const float* weights_dev;
+  float* g_kxy; float* loss_total; float grad_scale;   /* grad_scale 0 is read as 1 */
 } nnb_refstage_args;
 size_t nnb_refstage_workspace_bytes(int32_t h_d, int32_t w_d, int32_t pc_ratio);
 int nnb_refstage(const nnb_refstage_args* args, void* stream);

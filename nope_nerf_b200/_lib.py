@@ -34,7 +34,9 @@ class RefStageArgs(C.Structure):
     _fields_ = [("img_cur", _f), ("img_ref", _f), ("dpt_cur", _f), ("dpt_ref", _f), ("c2w_cur", _f), ("c2w_ref", _f), ("dist_cur", _f), ("dist_ref", _f),
                 ("H", C.c_int32), ("W", C.c_int32), ("h_d", C.c_int32), ("w_d", C.c_int32), ("pc_ratio", C.c_int32), ("is_last", C.c_int32),
                 ("flags", C.c_uint32), ("kx", C.c_float), ("ky", C.c_float), ("nearest_limit", C.c_float), ("w_pc", C.c_float), ("w_rgb_s", C.c_float),
-                ("losses", _f), ("g_c2w", _f), ("g_dist", _f), ("workspace", _f), ("workspace_bytes", C.c_size_t)]
+                ("losses", _f), ("g_c2w", _f), ("g_dist", _f), ("workspace", _f), ("workspace_bytes", C.c_size_t),
+                ("img_pp", _f), ("cam", _f), ("cam_idx_dev", _f), ("num_cams", C.c_int32), ("weights_dev", _f),
+                ("g_kxy", _f), ("loss_total", _f), ("grad_scale", C.c_float)]
 
 
 def _load():
@@ -55,7 +57,7 @@ def _load():
     lib.nnb_pose_bwd.argtypes = [_f, _f, _f, C.c_int32, _f, _f, _f, C.c_void_p]
     lib.nnb_loss_rgb_depth.argtypes = [_f, _f, _f, _f, C.c_int32, _f, _f, _f, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                        C.c_float, _f, _f, _f, _f, C.c_void_p]
-    lib.nnb_chamfer.argtypes = [_f, C.c_int32, _f, C.c_int32, _f, _f, _f, C.c_float, _f, _f, C.c_void_p]
+    lib.nnb_chamfer.argtypes = [_f, C.c_int32, _f, C.c_int32, _f, _f, _f, _f, C.c_float, _f, _f, C.c_void_p]
     lib.nnb_adam_step.argtypes = [_f, _f, _f, _f, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.nnb_profile_events.argtypes = [C.c_void_p, C.c_int32]
     lib.nnb_pose_fwd_dev.argtypes = [_f, _f, _f, _f, _f, C.c_void_p]
@@ -66,7 +68,7 @@ def _load():
     lib.nnb_counter_incr.argtypes = [_f, C.c_int32, C.c_void_p]
     lib.nnb_sample_pixels.argtypes = [_f, C.c_int32, C.c_int32, _f, C.c_void_p]
     lib.nnb_loss_rgb_depth_indirect.argtypes = [_f, _f, _f, C.c_int32, _f, _f, _f, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, _f, _f,
-                                                _f, _f, C.c_void_p]
+                                                _f, _f, _f, C.c_void_p]
     lib.nnb_refstage_workspace_bytes.restype = C.c_size_t
     lib.nnb_refstage_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.nnb_refstage.argtypes = [C.POINTER(RefStageArgs), C.c_void_p]

@@ -24,8 +24,9 @@ cudaError_t launch_adam_dev(float*, const float*, float*, float*, int64_t, const
 cudaError_t launch_incr(int*, int, cudaStream_t);
 cudaError_t launch_sample_pixels(const float*, int, int, long long*, cudaStream_t);
 cudaError_t launch_loss(const float*, const float*, const float*, const float* const*, const int64_t*, int, const float*, const float*, const uint8_t*,
-                        int, float, float, int, float, float*, float*, float*, float*, cudaStream_t);
-cudaError_t launch_chamfer(const float*, int, const float*, int, int*, int*, float*, float, float*, float*, cudaStream_t);
+                        int, float, float, int, float, float*, float*, float*, float*, const float*, cudaStream_t);
+cudaError_t launch_chamfer_full(const float*, int, const float*, int, unsigned long long*, unsigned long long*, float*, float, const float*, float*, float*,
+                                int*, int*, cudaStream_t);
 cudaError_t launch_adam(float*, const float*, float*, float*, int64_t, int, float, float, float, float, cudaStream_t);
 size_t refstage_workspace_bytes(int hd, int wd, int ratio);
 cudaError_t launch_refstage(const nnb_refstage_args& a, cudaStream_t st);
@@ -199,24 +200,25 @@ int nnb_loss_rgb_depth(const float* rgb, const float* rgb_gt, const float* img, 
   if (!rgb || !(rgb_gt || (img && ray_idx)) || !dp || !dg || !mask || !out || !g_rgb || !g_dp || !g_dg || N <= 0)
     return fail(-3, "nnb_loss_rgb_depth: bad arguments");
   cudaError_t e = launch_loss(rgb, rgb_gt, img, nullptr, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, rgb_l2, grad_scale, out, g_rgb, g_dp, g_dg,
-                              (cudaStream_t)stream);
+                              nullptr, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_loss_rgb_depth");
 }
 int nnb_loss_rgb_depth_indirect(const float* rgb, const float* const* img_pp, const int64_t* ray_idx, int32_t HW, const float* dp, const float* dg,
                                 const uint8_t* mask, int32_t N, float w_rgb, float w_depth, int32_t rgb_l2, float grad_scale, float* out,
-                                float* g_rgb, float* g_dp, float* g_dg, void* stream) {
+                                float* g_rgb, float* g_dp, float* g_dg, const float* w_dev, void* stream) {
   if (!rgb || !img_pp || !ray_idx || !dp || !dg || !mask || !out || !g_rgb || !g_dp || !g_dg || N <= 0)
     return fail(-3, "nnb_loss_rgb_depth_indirect: bad arguments");
   cudaError_t e = launch_loss(rgb, nullptr, nullptr, img_pp, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, rgb_l2, grad_scale, out, g_rgb, g_dp,
-                              g_dg, (cudaStream_t)stream);
+                              g_dg, w_dev, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_loss_rgb_depth_indirect");
 }
 
-int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, int32_t* ixy, int32_t* iyx, float* loss, float weight,
+int nnb_chamfer(const float* X, int32_t P, const float* Y, int32_t Q, uint64_t* keys, int32_t* ixy, int32_t* iyx, float* loss, float weight,
                 float* gX, float* gY, void* stream) {
-  if (!X || !Y || !ixy || !iyx || !loss || P <= 0 || Q <= 0 || ((gX == nullptr) != (gY == nullptr)))
+  if (!X || !Y || !keys || !loss || P <= 0 || Q <= 0 || ((gX == nullptr) != (gY == nullptr)) || ((ixy == nullptr) != (iyx == nullptr)))
     return fail(-3, "nnb_chamfer: bad arguments");
-  cudaError_t e = launch_chamfer(X, P, Y, Q, ixy, iyx, loss, weight, gX, gY, (cudaStream_t)stream);
+  cudaError_t e = launch_chamfer_full(X, P, Y, Q, reinterpret_cast<unsigned long long*>(keys), reinterpret_cast<unsigned long long*>(keys) + P, loss,
+                                      weight, nullptr, gX, gY, ixy, iyx, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_chamfer");
 }
 
@@ -227,8 +229,10 @@ size_t nnb_refstage_workspace_bytes(int32_t h_d, int32_t w_d, int32_t pc_ratio) 
 
 int nnb_refstage(const nnb_refstage_args* a, void* stream) {
   if (!a) return fail(-1, "null args");
-  if (!a->img_cur || !a->img_ref || !a->dpt_cur || !a->dpt_ref || !a->c2w_cur || !a->c2w_ref || !a->dist_cur || !a->dist_ref || !a->losses)
+  if ((!a->img_pp && (!a->img_cur || !a->img_ref)) || !a->dpt_cur || !a->dpt_ref || !a->c2w_cur || !a->c2w_ref || !a->dist_cur || !a->dist_ref ||
+      !a->losses)
     return fail(-3, "nnb_refstage: null pointer");
+  if (a->cam_idx_dev && a->num_cams <= 0) return fail(-3, "nnb_refstage: cam_idx_dev needs num_cams");
   if (a->H < 2 || a->W < 2 || a->pc_ratio <= 0 || a->h_d / a->pc_ratio < 2 || a->w_d / a->pc_ratio < 2)
     return fail(-2, "nnb_refstage: bad sizes");
   if (!a->workspace || a->workspace_bytes < refstage_workspace_bytes(a->h_d, a->w_d, a->pc_ratio)) return fail(-4, "nnb_refstage: workspace too small");

@@ -89,9 +89,10 @@ __device__ float block_sum(float v, float* sh) {
 
 __global__ void loss_rgb_depth_k(const float* rgb, const float* rgb_gt, const float* img, const float* const* img_pp, const int64_t* ray_idx, int HW,
                                  const float* dp, const float* dg, const uint8_t* mask, int N, float w_rgb, float w_depth,
-                                 int rgb_l2, float grad_scale, float* out, float* g_rgb, float* g_dp, float* g_dg) {
+                                 int rgb_l2, float grad_scale, float* out, float* g_rgb, float* g_dp, float* g_dg, const float* w_dev) {
   __shared__ float sh[33];
   if (img_pp) img = *img_pp;      // frame pointer fetched from device memory (lets a captured CUDA graph follow a new frame)
+  if (w_dev) { w_rgb = w_dev[0]; w_depth = w_dev[1]; }   // annealed weights (training.py:208-217) without re-capturing the graph
   float l1 = 0.f, l2 = 0.f, ld = 0.f, cnt = 0.f;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     for (int c = 0; c < 3; ++c) {
@@ -121,42 +122,98 @@ __global__ void loss_rgb_depth_k(const float* rgb, const float* rgb_gt, const fl
 }
 
 // ---- dense chamfer (model/losses.py:114-148) ---------------------------------------------
-// nearest neighbour of every a in A among B (ties -> first index), then mean |a - b_nn| and adjoints
-__global__ void nn_search_k(const float* A, int P, const float* B, int Q, int* idx) {
-  __shared__ float sb[256 * 3];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float ax = 0.f, ay = 0.f, az = 0.f;
-  if (i < P) { ax = A[3 * i]; ay = A[3 * i + 1]; az = A[3 * i + 2]; }
-  float best = INFINITY; int bi = 0;
-  for (int q0 = 0; q0 < Q; q0 += 256) {
-    int nq = min(256, Q - q0);
+// Brute-force nearest neighbour of every a in A among B (the reference materialises the (P,Q) distance matrix and takes
+// torch.argmin: ties -> first index), both directions in ONE launch, then mean |a - b_nn| and its adjoints.
+//   * SIMT fp32, 2 * P * Q pairs (P = Q = 16 128 at the 384x672 DPT map / pc_ratio 4: 520 M pairs, ~6 instructions each).
+//   * squared distances in the difference form (a-b)^2 (no cancellation, no sqrt per pair: the MUFU pipe is 1/4 rate); ordering
+//     by d^2 equals ordering by |a-b| and exact duplicates keep the first index.
+//   * packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): one thread owns 4 queries = 2 register pairs, the target comes from shared
+//     memory already duplicated (bx,bx | by,by | bz,bz) so every LDS feeds both pairs.
+//   * 2-D decomposition queries x target splits so that ~4 blocks per SM are resident; the per-split winners meet in a 64-bit
+//     atomicMin on (d^2 bits << 32 | index): smallest distance first, smallest index among equal distances.
+constexpr int NS_THREADS = 128, NS_QPT = 4, NS_CHUNK = 256;
+
+__device__ __forceinline__ unsigned long long pk2(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+__global__ void __launch_bounds__(NS_THREADS) nn_search_k(const float* __restrict__ X, int P, const float* __restrict__ Y, int Q,
+                                                          unsigned long long* kxy, unsigned long long* kyx, int per_split) {
+  const bool rev = blockIdx.z != 0;
+  const float* __restrict__ A = rev ? Y : X; const float* __restrict__ B = rev ? X : Y;
+  const int na = rev ? Q : P, nb = rev ? P : Q;
+  unsigned long long* keys = rev ? kyx : kxy;
+  if (blockIdx.x * (NS_THREADS * NS_QPT) >= na) return;
+  const int t0 = blockIdx.y * per_split, t1 = min(nb, t0 + per_split);
+  if (t0 >= t1) return;
+  __shared__ ulonglong2 sxy[NS_CHUNK];            // {(bx,bx), (by,by)}
+  __shared__ unsigned long long sz[NS_CHUNK];     // (bz,bz)
+  const int q0 = (blockIdx.x * NS_THREADS + threadIdx.x) * NS_QPT;
+  float a[NS_QPT][3];
+#pragma unroll
+  for (int j = 0; j < NS_QPT; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a[j][c] = (q0 + j < na) ? A[3 * (size_t)(q0 + j) + c] : 0.f;
+  const unsigned long long ax0 = pk2(a[0][0], a[1][0]), ay0 = pk2(a[0][1], a[1][1]), az0 = pk2(a[0][2], a[1][2]);
+  const unsigned long long ax1 = pk2(a[2][0], a[3][0]), ay1 = pk2(a[2][1], a[3][1]), az1 = pk2(a[2][2], a[3][2]);
+  float best[NS_QPT]; int bi[NS_QPT];
+#pragma unroll
+  for (int j = 0; j < NS_QPT; ++j) { best[j] = INFINITY; bi[j] = 0; }
+  for (int c0 = t0; c0 < t1; c0 += NS_CHUNK) {
+    const int n = min(NS_CHUNK, t1 - c0);
     __syncthreads();
-    for (int k = threadIdx.x; k < nq * 3; k += blockDim.x) sb[k] = B[3 * q0 + k];
+    for (int k = threadIdx.x; k < n; k += NS_THREADS) {
+      const float bx = B[3 * (size_t)(c0 + k)], by = B[3 * (size_t)(c0 + k) + 1], bz = B[3 * (size_t)(c0 + k) + 2];
+      sxy[k] = make_ulonglong2(pk2(bx, bx), pk2(by, by)); sz[k] = pk2(bz, bz);
+    }
     __syncthreads();
-    for (int q = 0; q < nq; ++q) {
-      float dx = __fsub_rn(ax, sb[3 * q]), dy = __fsub_rn(ay, sb[3 * q + 1]), dz = __fsub_rn(az, sb[3 * q + 2]);
-      float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-      if (d < best) { best = d; bi = q0 + q; }
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) {
+      const ulonglong2 u = sxy[k]; const unsigned long long w = sz[k];
+      unsigned long long dx = sub2(ax0, u.x), dy = sub2(ay0, u.y), dz = sub2(az0, w);
+      const unsigned long long e0 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+      dx = sub2(ax1, u.x); dy = sub2(ay1, u.y); dz = sub2(az1, w);
+      const unsigned long long e1 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+      float d[NS_QPT];
+      upk2(e0, d[0], d[1]); upk2(e1, d[2], d[3]);
+#pragma unroll
+      for (int j = 0; j < NS_QPT; ++j) if (d[j] < best[j]) { best[j] = d[j]; bi[j] = c0 + k; }
     }
   }
-  if (i < P) idx[i] = bi;
+#pragma unroll
+  for (int j = 0; j < NS_QPT; ++j)
+    if (q0 + j < na) atomicMin(keys + q0 + j, ((unsigned long long)__float_as_uint(best[j]) << 32) | (unsigned)bi[j]);
 }
-__global__ void chamfer_acc_k(const float* A, int P, const float* B, const int* idx, float weight, float* loss, float* gA, float* gB) {
+// loss += mean |a - b_nn| (+ the other direction), adjoints scattered with atomics; weight from device memory when weight_dev
+__global__ void chamfer_acc_k(const float* X, int P, const float* Y, int Q, const unsigned long long* kxy, const unsigned long long* kyx,
+                              float weight, const float* weight_dev, float* loss, float* gX, float* gY, int* ixy, int* iyx) {
   __shared__ float sh[33];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool rev = i0 >= P; const int i = rev ? i0 - P : i0;
+  const float* A = rev ? Y : X; const float* B = rev ? X : Y; const int na = rev ? Q : P;
+  float* gA = rev ? gY : gX; float* gB = rev ? gX : gY;
+  if (weight_dev) weight = *weight_dev;
   float dist = 0.f;
-  if (i < P) {
-    int j = idx[i];
+  if (i0 < P + Q) {
+    const int j = (int)(unsigned)((rev ? kyx : kxy)[i] & 0xffffffffull);
+    if (ixy) (rev ? iyx : ixy)[i] = j;
     float vx = A[3 * i] - B[3 * j], vy = A[3 * i + 1] - B[3 * j + 1], vz = A[3 * i + 2] - B[3 * j + 2];
     dist = sqrtf(vx * vx + vy * vy + vz * vz);
     if (gA && dist > 0.f) {
-      float s = weight / (dist * (float)P);
+      float s = weight / (dist * (float)na);
       atomicAdd(gA + 3 * i, s * vx); atomicAdd(gA + 3 * i + 1, s * vy); atomicAdd(gA + 3 * i + 2, s * vz);
       atomicAdd(gB + 3 * j, -s * vx); atomicAdd(gB + 3 * j + 1, -s * vy); atomicAdd(gB + 3 * j + 2, -s * vz);
     }
+    dist /= (float)na;
   }
+  // blocks never straddle the two directions' normalisation because dist is already divided by its own count
   float tot = block_sum(dist, sh);
-  if (threadIdx.x == 0) atomicAdd(loss, tot / (float)P);
+  if (threadIdx.x == 0) atomicAdd(loss, tot);
 }
 
 // Learn_Distortion.forward (model/distortions.py:19-27) for a device-resident camera index:
@@ -294,17 +351,33 @@ cudaError_t launch_sample_pixels(const float* u, int HW, int N, long long* out, 
 cudaError_t launch_incr(int* a, int n, cudaStream_t st) { incr_k<<<1, 32, 0, st>>>(a, n); return cudaGetLastError(); }
 cudaError_t launch_loss(const float* rgb, const float* rgb_gt, const float* img, const float* const* img_pp, const int64_t* ray_idx, int HW,
                         const float* dp, const float* dg, const uint8_t* mask, int N, float w_rgb, float w_depth, int l2, float gscale, float* out,
-                        float* g_rgb, float* g_dp, float* g_dg, cudaStream_t st) {
-  loss_rgb_depth_k<<<1, 1024, 0, st>>>(rgb, rgb_gt, img, img_pp, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, l2, gscale, out, g_rgb, g_dp, g_dg);
+                        float* g_rgb, float* g_dp, float* g_dg, const float* w_dev, cudaStream_t st) {
+  loss_rgb_depth_k<<<1, 1024, 0, st>>>(rgb, rgb_gt, img, img_pp, ray_idx, HW, dp, dg, mask, N, w_rgb, w_depth, l2, gscale, out, g_rgb, g_dp, g_dg,
+                                       w_dev);
   return cudaGetLastError();
 }
-cudaError_t launch_chamfer(const float* X, int P, const float* Y, int Q, int* ixy, int* iyx, float* loss, float weight, float* gX,
-                           float* gY, cudaStream_t st) {
-  nn_search_k<<<(P + 255) / 256, 256, 0, st>>>(X, P, Y, Q, ixy);
-  nn_search_k<<<(Q + 255) / 256, 256, 0, st>>>(Y, Q, X, P, iyx);
-  chamfer_acc_k<<<(P + 255) / 256, 256, 0, st>>>(X, P, Y, ixy, weight, loss, gX, gY);
-  chamfer_acc_k<<<(Q + 255) / 256, 256, 0, st>>>(Y, Q, X, iyx, weight, loss, gY, gX);
+// keys: caller scratch, 64-bit per point (P + Q entries); optional int32 index outputs for the C ABI
+cudaError_t launch_chamfer_full(const float* X, int P, const float* Y, int Q, unsigned long long* kxy, unsigned long long* kyx, float* loss,
+                                float weight, const float* weight_dev, float* gX, float* gY, int* ixy, int* iyx, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(kxy, 0xff, sizeof(unsigned long long) * (size_t)P, st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(kyx, 0xff, sizeof(unsigned long long) * (size_t)Q, st);
+  if (e != cudaSuccess) return e;
+  const int per_block = NS_THREADS * NS_QPT, mx = P > Q ? P : Q;
+  const int bx = (mx + per_block - 1) / per_block;
+  int splits = (2 * 148 + bx - 1) / bx;                       // ~4 resident blocks per SM over both directions
+  const int mn = P < Q ? P : Q;
+  if (splits > (mn + NS_CHUNK - 1) / NS_CHUNK) splits = (mn + NS_CHUNK - 1) / NS_CHUNK;
+  if (splits < 1) splits = 1;
+  int per_split = (mx + splits - 1) / splits;
+  per_split = (per_split + 3) & ~3;
+  nn_search_k<<<dim3(bx, splits, 2), NS_THREADS, 0, st>>>(X, P, Y, Q, kxy, kyx, per_split);
+  chamfer_acc_k<<<(P + Q + 255) / 256, 256, 0, st>>>(X, P, Y, Q, kxy, kyx, weight, weight_dev, loss, gX, gY, ixy, iyx);
   return cudaGetLastError();
+}
+cudaError_t launch_chamfer_dev(const float* X, int P, const float* Y, int Q, unsigned long long* kxy, unsigned long long* kyx, float* loss,
+                               const float* weight_dev, float* gX, float* gY, cudaStream_t st) {
+  return launch_chamfer_full(X, P, Y, Q, kxy, kyx, loss, 1.f, weight_dev, gX, gY, nullptr, nullptr, st);
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2, float eps, cudaStream_t st) {
   double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);

@@ -1,8 +1,7 @@
 // Reference-image stage of Trainer.compute_loss (model/training.py:280-365): per-point arithmetic of the point-cloud
 // (chamfer) and warped-RGB terms, written as __host__ __device__ functions so the SAME code is checked on the CPU against
 // oracle.ref_stage (tests/test_host.py builds tools/refstage_host_check.cu with nvcc) and runs inside the kernels of
-// nnb_refstage.cu.  EXPERIMENTAL in round 1: the kernels have not run on hardware yet; model/training.py keeps the torch
-// statement of this stage unless Trainer(native_ref_stage=True).
+// nnb_refstage.cu (GPU parity: tests/test_gpu_parity.py::test_native_ref_stage_vs_oracle and the full-loss trainer goldens).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -21,8 +20,10 @@ struct Geom {            // everything a point needs besides the image / depth p
   float s_cur, h_cur, s_ref, h_ref;   // effective distortion (scale, shift) of the current / reference view
   float M[12];                   // relative transform [R | t] (row-major 3 x 4), training.py:296-313
   float s2;                      // scale both clouds are divided by (scale_pcs), training.py:357-359
-  int is_last, scale_pcs, detach_rgbs_scale;
+  int is_last, scale_pcs, detach_rgbs_scale, shift_first;
+  float w_pc, w_rgb_s;           // loss weights (annealed per epoch, training.py:208-217)
 };
+constexpr int kAcc = 17;         // reduced sums: gR (9) | gt (3) | g_s2 | g_scale_cur | g_shift_cur | g_kx | g_ky
 
 // F.interpolate(..., mode='nearest') source index: floor(dst * in/out), scale in float32 (training.py:318-319)
 NNB_HD int nearest_src(int dst, int n_in, int n_out) {
@@ -82,7 +83,9 @@ NNB_HD void point_forward(const Geom& G, const float* dpt_cur, const float* dpt_
   p.px = 2.f * (float)col / (float)(G.rw - 1) - 1.f; p.py = 2.f * (float)row / (float)(G.rh - 1) - 1.f;
   const int sr = nearest_src(row, G.hd, G.rh), sc = nearest_src(col, G.wd, G.rw);
   p.raw_cur = dpt_cur[(size_t)sr * G.wd + sc];
-  float dc = p.raw_cur * G.s_cur + G.h_cur, dr = dpt_ref[(size_t)sr * G.wd + sc] * G.s_ref + G.h_ref;   // training.py:241-245, 283-287
+  const float raw_ref = dpt_ref[(size_t)sr * G.wd + sc];
+  float dc = G.shift_first ? (p.raw_cur + G.h_cur) * G.s_cur : p.raw_cur * G.s_cur + G.h_cur;           // training.py:241-245
+  float dr = G.shift_first ? (raw_ref + G.h_ref) * G.s_ref : raw_ref * G.s_ref + G.h_ref;               // training.py:283-287
   p.live_cur = dc >= G.nl;
   if (!p.live_cur) dc = G.nl;                                                                          // d[d < nl] = nl (training.py:320-321)
   if (dr < G.nl) dr = G.nl;
@@ -106,9 +109,9 @@ NNB_HD void point_rgb_diff(const Geom& G, const float* img1, const float* img2, 
 }
 
 // Adjoint of one point.  gXs, gYs: d(w_pc * chamfer) / d(scaled clouds) of this point (already weighted); inv_nv: w_rgb_s /
-// (3 * #valid) or 0.  Accumulates into acc[15] = { gR (9, row-major), gt (3), g_s2, g_scale_cur, g_shift_cur }.
+// (3 * #valid) or 0.  Accumulates into acc[kAcc] = { gR (9, row-major), gt (3), g_s2, g_scale_cur, g_shift_cur, g_kx, g_ky }.
 NNB_HD void point_backward(const Geom& G, const float* img1, const float* img2, const Point& p, const float gXs[3], const float gYs[3],
-                           float inv_nv, float acc[15]) {
+                           float inv_nv, float acc[kAcc]) {
   float gX[3] = {0.f, 0.f, 0.f}, gXr[3] = {0.f, 0.f, 0.f}, gY[3];
   const float s2 = G.scale_pcs ? G.s2 : 1.f;
   float gs2 = 0.f;
@@ -121,6 +124,10 @@ NNB_HD void point_backward(const Geom& G, const float* img1, const float* img2, 
     point_rgb_diff(G, img1, img2, p, diff);
     for (int c = 0; c < 3; ++c) gp[c] = (fabsf(diff[c]) < 1.f) ? -(diff[c] > 0.f ? 1.f : (diff[c] < 0.f ? -1.f : 0.f)) * inv_nv : 0.f;
     sample_lowres(img2, G, p.xy[0], p.xy[1], dummy, gp, gxy);
+    {                                                      // xy = (kx Xc_x, ky Xc_y) / z: the projection's own d/dK (also for fixed-up points)
+      const float z = -p.Xc[2];
+      acc[15] += gxy[0] * p.Xc[0] / z; acc[16] += gxy[1] * p.Xc[1] / z;
+    }
     if (!p.bad) {
       const float z = -p.Xc[2];
       gXr[0] = gxy[0] * G.kx / z; gXr[1] = gxy[1] * G.ky / z;
@@ -139,7 +146,11 @@ NNB_HD void point_backward(const Geom& G, const float* img1, const float* img2, 
   const float* gd_src = G.is_last ? gY : gpc1;          // which cloud was built from the current view's depth
   float gd = gd_src[0] * p.px / G.kx + gd_src[1] * p.py / G.ky - gd_src[2];
   if (!p.live_cur) gd = 0.f;
-  acc[13] += gd * p.raw_cur; acc[14] += gd;
+  if (G.shift_first) { acc[13] += gd * (p.raw_cur + G.h_cur); acc[14] += gd * G.s_cur; }
+  else { acc[13] += gd * p.raw_cur; acc[14] += gd; }
+  // back-projection (x d / kx, y d / ky, -d): d pc_x / d kx = -pc_x / kx, for both clouds
+  acc[15] -= (gpc1[0] * p.pc1[0] + gY[0] * p.pc2[0]) / G.kx;
+  acc[16] -= (gpc1[1] * p.pc1[1] + gY[1] * p.pc2[1]) / G.ky;
 }
 
 // rigid inverse of a 4x4 pose [R t; 0 1]
@@ -167,7 +178,7 @@ NNB_HD void prepare(Geom& G, const float* c2w_cur, const float* c2w_ref) {
 }
 
 // reduced sums acc[15] -> gradients w.r.t. the current view's c2w (16, row-major), effective scale and shift
-NNB_HD void finish(const Geom& G, const float* c2w_cur, const float* c2w_ref, const float acc[15], float g_c2w[16], float* g_scale, float* g_shift) {
+NNB_HD void finish(const Geom& G, const float* c2w_cur, const float* c2w_ref, const float acc[kAcc], float g_c2w[16], float* g_scale, float* g_shift) {
   float gM[16], inv[16], invT[16], tmp[16], tmp2[16];
   for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) gM[4 * r + c] = acc[3 * r + c]; gM[4 * r + 3] = acc[9 + r]; }
   gM[12] = gM[13] = gM[14] = gM[15] = 0.f;

@@ -10,13 +10,13 @@ Gradients land in ONE flat fp32 buffer [MLP | r | t | scales | shifts | 4 loss s
 slices are installed as every parameter's .grad, so (a) train.py's own torch.optim.Adam
 instances step unchanged and (b) data-parallel training is a single NCCL all-reduce of that
 buffer per step.  The point-cloud / warped-RGB terms of the reference-image
-stage (training.py:280-365) run as torch ops + nnb_chamfer and accumulate into the same buffer.
+stage (training.py:280-365) are ONE more library call (nnb_refstage: forward + adjoint) whose pose /
+distortion gradients accumulate into the same buffer.
 """
 import logging
 import os
 import numpy as np
 import torch
-from torch.nn import functional as F
 from .. import ops
 from .. import _lib as L
 from .losses import Loss
@@ -40,10 +40,29 @@ class _FlatAdam:
         self.ok = self._supported()
         self.nsteps = 0              # steps taken so far (source of truth shared with the CUDA-graph path)
         self._synced = True
+        self._loaded = False         # optimizer.load_state_dict() happened since the last step: adopt ITS step count
         try:
             optimizer.register_state_dict_pre_hook(lambda opt: self.sync_step_tensors())
         except Exception:
             pass
+        try:
+            optimizer.register_load_state_dict_post_hook(lambda opt: self._mark_loaded())
+        except Exception:
+            pass
+
+    def _mark_loaded(self):
+        self._loaded = True
+
+    def adopt_loaded_step(self):
+        """torch.optim.Adam continues bias correction from the loaded 'step' (checkpoint resume, train.py:60-67); so do we"""
+        st0 = next((st for st in self.opt.state.values() if 'step' in st), None)
+        if st0 is None:
+            return
+        if self._loaded:
+            self.nsteps = int(st0['step']); self._synced = True
+        elif self._synced and int(st0['step']) > self.nsteps:
+            self.nsteps = int(st0['step'])
+        self._loaded = False
 
     def sync_step_tensors(self):
         """optimizer.state[p]['step'] tensors follow `nsteps` lazily (the graph path does not touch them per step)"""
@@ -68,9 +87,7 @@ class _FlatAdam:
                 if key not in self.m or self.m[key].shape != p.shape or self.m[key].device != p.device:
                     self.m[key] = torch.zeros_like(p); self.v[key] = torch.zeros_like(p)
                 self._state(p, self.m[key], self.v[key])
-        st0 = next(iter(self.opt.state.values()), None)
-        if st0 is not None and self._synced and int(st0['step']) > self.nsteps:
-            self.nsteps = int(st0['step'])          # e.g. optimizer state loaded from a checkpoint
+        self.adopt_loaded_step()                     # e.g. optimizer state loaded from a checkpoint
 
     def _supported(self):
         o = self.opt
@@ -98,6 +115,8 @@ class _FlatAdam:
         params = [p for p in g['params'] if p.requires_grad and p.grad is not None]
         if not self.ok or not params:
             return self.opt.step()
+        if self._loaded or (self._synced and self.nsteps == 0):
+            self.adopt_loaded_step()
         lr, (b1, b2), eps = g['lr'], g['betas'], g['eps']
         if self.flat_param is not None:
             flat = self.flat_param()
@@ -110,7 +129,6 @@ class _FlatAdam:
             if self.m is None or self.m.device != flat.device:
                 self.m = torch.zeros(n, device=flat.device); self.v = torch.zeros(n, device=flat.device)
             sts = [self._state(p, self.m[o:o + k].view(sh), self.v[o:o + k].view(sh)) for p, (o, k, sh) in zip(plist, self.flat_slices)]
-            if not self._synced or int(sts[0]['step']) != self.nsteps: self.sync_step_tensors()
             step = self.nsteps + 1
             gflat_ptr_ok = all(p.grad is not None and p.grad.data_ptr() == g0.data_ptr() + 4 * o for p, (o, k, sh) in zip(plist, self.flat_slices))
             if not gflat_ptr_ok:
@@ -143,19 +161,20 @@ def _host_diag_check(camera_mat):
 
 
 class _GraphStep:
-    """The whole render-only training step (pose exp-map, distortion, pixel sampling, render forward, losses, backward,
-    [all-reduce], Adam x3) captured ONCE as a CUDA graph and replayed per frame.  Everything that changes from step to
-    step is read from device memory: camera index, frame pointer, DPT map, camera matrix, Adam step counters, learning
-    rates.  The first call runs the same body eagerly (that IS that call's training step and warms every lazy
-    initialisation), the second call captures, later calls replay."""
+    """The whole training step (pose exp-map, distortion, pixel sampling, render forward, losses, [reference-image stage],
+    backward, [all-reduce], Adam x3) captured ONCE as a CUDA graph and replayed per frame.  Everything that changes from step
+    to step is read from device memory: camera indices, frame pointers, DPT maps, camera matrix, loss weights (annealed per
+    epoch), Adam step counters, learning rates.  The first call runs the same body eagerly (that IS that call's training step and
+    warms every lazy initialisation), the second call captures, later calls replay.  With `use_ref` the reference-image stage
+    (point-cloud + warped-RGB terms, training.py:280-365) runs on a forked stream beside the render forward / backward."""
 
-    def __init__(self, tr, h, w, hd, wd, w_rgb, w_depth, rgb_l2):
-        self.tr = tr; self.key = (h, w, hd, wd, float(w_rgb), float(w_depth), bool(rgb_l2))
+    def __init__(self, tr, h, w, hd, wd, rgb_l2, use_ref):
+        self.tr = tr; self.key = (h, w, hd, wd, bool(rgb_l2), bool(use_ref))
         dev = tr.device
         self.h, self.w, self.hd, self.wd = h, w, hd, wd
-        self.w_rgb, self.w_depth, self.rgb_l2 = w_rgb, w_depth, rgb_l2
+        self.rgb_l2, self.use_ref = bool(rgb_l2), bool(use_ref)
         self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.imgp = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.imgpp = torch.zeros(2, dtype=torch.int64, device=dev)        # frame pointers {current, reference}
         self.dpt = torch.zeros(hd, wd, device=dev)
         self.cam = torch.zeros(4, 4, device=dev); self.cam_host = None
         self.ss = torch.zeros(2, device=dev)               # effective (scale, shift) of the current view
@@ -163,19 +182,30 @@ class _GraphStep:
         self.small = torch.zeros(16 + 2, device=dev)       # [g_c2w | g_scale_shift]
         self.steps = torch.zeros(3, dtype=torch.int32, device=dev)   # Adam step counters: mlp, pose, distortion
         self.lrs = torch.zeros(3, device=dev); self.lr_host = [None, None, None]
+        self.wts = torch.zeros(4, device=dev); self.wts_host = None  # {w_rgb, w_depth, w_pc, w_rgb_s}
         self.out4 = torch.zeros(4, device=dev)
         N = tr.n_training_points // tr.world if tr.dp_mode == 'rays' else tr.n_training_points
         self.g_rgb = torch.zeros(N, 3, device=dev); self.g_dp = torch.zeros(N, device=dev); self.g_dg = torch.zeros(N, device=dev)
-        self.graph = None; self.calls = 0; self.keep = []; self.img_ref = None
+        self.graph = None; self.calls = 0; self.keep = []; self.host_refs = []; self.dev_refs = None
+        self.rs_losses = torch.zeros(2, device=dev)        # {loss_pc, loss_rgb_s} of the reference-image stage (full-loss steps)
+        self.rs_total = torch.zeros(1, device=dev)
+        if self.use_ref:
+            self.idx_ref = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.dpt_ref = torch.zeros(hd, wd, device=dev)
+            self.c2w_ref = torch.zeros(4, 4, device=dev); self.ss_ref = torch.zeros(2, device=dev)
+            nbytes = L.lib.nnb_refstage_workspace_bytes(hd, wd, int(tr.pc_ratio))
+            if nbytes == 0:
+                raise ValueError("reference-image stage: DPT map %dx%d too small for pc_ratio %d" % (hd, wd, tr.pc_ratio))
+            self.rs_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.side = torch.cuda.Stream(device=dev)
+            self.stage = None                              # device staging of host frames (2,3,h,w), allocated on first use
         self.fadams = None
 
     def _adams(self):
         tr = self.tr
         if self.fadams is None:
-            from .official_nerf import PARAM_SLICES
-            net = tr.model.renderer.model
-            fa = [tr._fadam_for(tr.optimizer, True), tr._fadam_for(tr.optimizer_pose, False), tr._fadam_for(tr.optimizer_distortion, False)]
-            self.fadams = fa
+            self.fadams = [tr._fadam_for(tr.optimizer, True), tr._fadam_for(tr.optimizer_pose, False),
+                           tr._fadam_for(tr.optimizer_distortion, False)]
         return self.fadams
 
     def eligible_optimizers(self):
@@ -194,6 +224,22 @@ class _GraphStep:
         self.small.zero_()
         g_c2w = self.small[:16].view(4, 4); g_ss = self.small[16:18]
         ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx, dnet.fix_scaleN, self.ss)
+        init = None if pose.init_c2w is None else pose.init_c2w.detach()
+        ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx, self.c2w)
+        gs = 1.0 / tr.world
+        if self.use_ref:
+            # reference-image stage on a forked stream: it only needs the two poses / distortions / frames, and accumulates its
+            # pose / distortion gradients (atomics) into the buffers the render backward also accumulates into
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx_ref, self.c2w_ref)
+                ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx_ref, dnet.fix_scaleN, self.ss_ref)
+                self.rs_total.zero_()
+                ops.refstage_raw(self.c2w, self.ss, self.c2w_ref, self.ss_ref, self.dpt, self.dpt_ref, H=h, W=w, img_pp=self.imgpp, cam=self.cam,
+                                 cam_idx_dev=self.idx, num_cams=pose.num_cams, weights_dev=self.wts[2:4], nearest_limit=tr.nearest_limit,
+                                 pc_ratio=tr.pc_ratio, scale_pcs=tr.scale_pcs, detach_rgbs_scale=tr.detach_rgbs_scale, shift_first=tr.shift_first,
+                                 losses=self.rs_losses, g_c2w=g_c2w, g_dist=g_ss, loss_total=self.rs_total, grad_scale=gs, workspace=self.rs_ws)
         n_points = tr.n_training_points
         if tr.pixel_sampler == 'randperm' or (tr.pixel_sampler == 'auto' and not tr.use_cuda_graph) or n_points > min(h * w // 2, 8192):
             ray_idx = torch.randperm(h * w, device=dev)[:n_points]                # training.py:257 (reference RNG stream)
@@ -207,27 +253,28 @@ class _GraphStep:
             ray_idx = ray_idx[tr.rank::tr.world].contiguous()
             if noise is not None: noise = noise[tr.rank::tr.world].contiguous()
         n_local = ray_idx.shape[0]
-        init = None if pose.init_c2w is None else pose.init_c2w.detach()
-        ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx, self.c2w)
         flags = ops.flags_from_cfg(rend.cfg, net.occ_activation, eval_=False, shift_first=tr.shift_first)
         ndc = rend.cfg['sample_option'] == 'ndc'
         call = ops.RenderCall(net.flat_weights(), self.c2w, self.cam, N=n_local, S=S, flags=flags,
                               engine=rend.engine if rend.engine is not None else ops.default_engine(),
                               near=0.0 if ndc else rend.depth_range[0], far=1.0 if ndc else rend.depth_range[1],
                               ray_idx=ray_idx, depth_map=self.dpt, scale=self.ss[0:1], shift=self.ss[1:2], noise=noise, H=h, W=w, stash=True)
-        gs = 1.0 / tr.world
-        ops.loss_rgb_depth_indirect(call.rgb, call.depth_pred, call.depth_gt, call.mask, self.w_rgb, self.w_depth, self.rgb_l2, self.imgp,
-                                    ray_idx, h * w, self.out4, self.g_rgb, self.g_dp, self.g_dg, grad_scale=gs)
+        ops.loss_rgb_depth_indirect(call.rgb, call.depth_pred, call.depth_gt, call.mask, 0.0, 0.0, self.rgb_l2, self.imgpp,
+                                    ray_idx, h * w, self.out4, self.g_rgb, self.g_dp, self.g_dg, grad_scale=gs, w_dev=self.wts)
         ws = call.ws
         call.pooled = False                                 # memory referenced by a captured graph never returns to the pool
         call.backward(self.g_rgb, self.g_dp, None if tr.detach_gt_depth else self.g_dg, gbuf[:L.NUM_PARAMS], g_c2w, None, None, g_ss)
         self.keep.append((call, ws, ray_idx, noise))        # graph-owned memory stays referenced (and out of the workspace pool)
+        if self.use_ref:
+            torch.cuda.current_stream().wait_stream(self.side)
         ops.pose_bwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx, g_c2w,
                          gv['r'] if pose.r.requires_grad else None, gv['t'] if pose.t.requires_grad else None)
         ops.distortion_bwd_dev(dnet.global_scales.detach(), self.idx, dnet.fix_scaleN, g_ss,
                                gv['scales'] if dnet.global_scales.requires_grad else None,
                                gv['shifts'] if dnet.global_shifts.requires_grad else None)
         gv['losses'].copy_(self.out4 * gs if tr.world > 1 else self.out4)
+        if self.use_ref:
+            gv['losses'][0:1].add_(self.rs_total, alpha=gs)
 
     def reduce(self):
         tr = self.tr
@@ -250,15 +297,34 @@ class _GraphStep:
                 if p.requires_grad and p.grad is not None:
                     ops.adam_step_dev(p.data, p.grad, fa.m[id(p)], fa.v[id(p)], self.steps[k:k + 1], self.lrs[k:k + 1], b1, b2, g['eps'])
 
-    def run(self, data):
+    def _frame_ptr(self, t, slot):
+        """device pointer of a (1,3,h,w) frame: device tensors and page-locked host tensors are used in place (render-only steps read
+        N pixels of them); full-loss steps bilinearly resample both whole frames, so host frames are staged in HBM first"""
+        dev = self.tr.device
+        if t.device.type == 'cpu' and (self.use_ref or not t.is_pinned()):
+            if self.use_ref:
+                if self.stage is None:
+                    self.stage = torch.empty(2, 3, self.h, self.w, device=dev)
+                self.stage[slot].copy_(t.reshape(3, self.h, self.w), non_blocking=True)
+                return self.stage[slot], t
+            t = t.to(dev, non_blocking=True)
+        return t, t
+
+    def run(self, data, wts):
         tr = self.tr; dev = tr.device
-        img = data.get('img')
-        if img.device.type == 'cpu' and not img.is_pinned():
-            img = img.to(dev, non_blocking=True)
-        self.img_ref = img
-        self.imgp.fill_(img.data_ptr())
+        img, img_keep = self._frame_ptr(data.get('img'), 0)
+        ptrs = [img.data_ptr(), 0]
+        keep = [img_keep]
         self.idx.fill_(int(data.get('img.idx')))
         self.dpt.copy_(data.get('img.dpt').reshape(self.hd, self.wd), non_blocking=True)
+        if self.use_ref:
+            ref, ref_keep = self._frame_ptr(data.get('img.ref_imgs'), 1)
+            ptrs[1] = ref.data_ptr(); keep.append(ref_keep)
+            self.idx_ref.fill_(int(data.get('img.ref_idxs')))
+            self.dpt_ref.copy_(data.get('img.ref_dpts').reshape(self.hd, self.wd), non_blocking=True)
+        if getattr(self, 'ptrs_host', None) != ptrs:
+            self.imgpp.copy_(torch.tensor(ptrs, dtype=torch.int64)); self.ptrs_host = ptrs
+        self.dev_refs = keep
         cm = data.get('img.camera_mat')
         if self.cam_host is None or (cm.device.type == 'cpu' and not torch.equal(cm.reshape(4, 4), self.cam_host)):
             _host_diag_check(cm)
@@ -266,6 +332,8 @@ class _GraphStep:
             self.cam.copy_(cm.reshape(4, 4))
         elif cm.device.type != 'cpu':
             self.cam.copy_(cm.reshape(4, 4))
+        if self.wts_host != wts:
+            self.wts.copy_(torch.tensor(wts, dtype=torch.float32)); self.wts_host = list(wts)
         fas = self._adams()
         opts = (tr.optimizer, tr.optimizer_pose, tr.optimizer_distortion)
         for k, (fa, opt) in enumerate(zip(fas, opts)):
@@ -285,7 +353,7 @@ class _GraphStep:
                 torch.cuda.synchronize()
                 # world == 1: one graph for the whole step.  world > 1: the NCCL all-reduce stays an eager call between two
                 # graphs (gradients | optimizers); thread_local because the NCCL watchdog thread touches the CUDA API
-                self.graph = torch.cuda.CUDAGraph()
+                self.graph = torch.cuda.CUDAGraph(keep_graph=True) if tr.keep_graph else torch.cuda.CUDAGraph()
                 if tr.world == 1:
                     with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                         self.body()
@@ -302,11 +370,20 @@ class _GraphStep:
         for fa in fas:
             fa.nsteps += 1; fa._synced = False
         self.steps_host = [fa.nsteps for fa in fas]
-        gv_losses = tr._gbuf[-4:]
-        zero = torch.zeros((), device=dev)
-        return {'loss': gv_losses[0], 'loss_rgb': gv_losses[1], 'loss_depth': gv_losses[2], 'l2_mean': gv_losses[3],
-                'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': zero, 'loss_rgb_s': zero, 'loss_depth_consistency': zero,
-                'scale': self.ss[0:1], 'shift': self.ss[1:2]}
+        if any(t.device.type == 'cpu' for t in keep):
+            # a page-locked host frame is read IN PLACE (or copied asynchronously) by this step: keep it referenced until the step has
+            # run (torch's pinned-memory allocator only tracks torch-issued copies, so a recycled DataLoader buffer could be refilled)
+            ev = torch.cuda.Event(); ev.record()
+            self.host_refs.append((keep, ev))
+            while len(self.host_refs) > 1 and self.host_refs[0][1].query():
+                self.host_refs.pop(0)
+        # per-call snapshot (ONE small kernel): later steps overwrite the persistent buffers the graph writes to, and train.py
+        # keeps loss_dict['scale'/'shift'] per view (train.py:215-216)
+        snap = torch.cat([tr._gbuf[-4:], self.ss, self.rs_losses])
+        zero = snap.new_zeros(())
+        return {'loss': snap[0], 'loss_rgb': snap[1], 'loss_depth': snap[2], 'l2_mean': snap[3],
+                'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': snap[6] if wts[2] != 0.0 else zero,
+                'loss_rgb_s': snap[7] if wts[3] != 0.0 else zero, 'loss_depth_consistency': zero, 'scale': snap[4:5], 'shift': snap[5:6]}
 
 
 class Trainer(object):
@@ -351,6 +428,9 @@ class Trainer(object):
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(self.dp_group)
             self.rank = torch.distributed.get_rank(self.dp_group)
+        if self.world > 1 and self.dp_mode == 'rays' and self.n_training_points % self.world != 0:
+            raise ValueError("dp_mode='rays': training.n_training_points (%d) must be a multiple of the world size (%d): every rank "
+                             "takes ray_idx[rank::world] and the loss normalisation assumes equal shards" % (self.n_training_points, self.world))
         self._gbuf = None
         self._pix_cache = {}
         # fused flat-buffer Adam; optimizers remain the caller's objects
@@ -361,11 +441,10 @@ class Trainer(object):
         if self.world > 1 and os.environ.get('NNB_GRAPH_DP', '1') != '1':
             self.use_cuda_graph = False      # data parallel: two graphs around an eager NCCL all-reduce (NNB_GRAPH_DP=0 disables)
         self._gsteps = {}
+        self.keep_graph = bool(kwargs.get('keep_graph', False))      # keep the cudaGraph_t for introspection (bench.py counts its nodes)
         # 'randperm' = the reference's torch.randperm(H*W)[:N] (identical RNG stream in eager mode); 'hash' = nnb_sample_pixels;
         # 'auto' = randperm when running eagerly, hash inside the CUDA graph (whose RNG stream differs from eager anyway)
         self.pixel_sampler = kwargs.get('pixel_sampler', 'auto')
-        # EXPERIMENTAL (round 1): the reference-image stage as fused CUDA kernels (nnb_refstage) instead of the torch statement
-        self.native_ref_stage = bool(kwargs.get('native_ref_stage', False))
 
     # ------------------------------------------------------------------------------------
     def _grad_buffer(self):
@@ -401,7 +480,7 @@ class Trainer(object):
         if self.distortion_net: self.distortion_net.train()
         gs = self._graph_step_or_none(data, epoch, scheduling_start)
         if gs is not None:
-            return gs.run(data)          # fixed kernel sequence; replayed as one CUDA graph when use_cuda_graph
+            return gs[0].run(data, gs[1])          # fixed kernel sequence; replayed as one CUDA graph when use_cuda_graph
         loss_dict = self.compute_loss(data, it=it, epoch=epoch, scheduling_start=scheduling_start,
                                       out_render_path=render_path, backward=True)
         self._opt_step(self.optimizer, mlp=True)
@@ -428,7 +507,8 @@ class Trainer(object):
         self._fadam_for(opt, mlp).step()
 
     def _graph_step_or_none(self, data, epoch, scheduling_start):
-        """fast path: the whole step as one fixed kernel sequence / CUDA graph (render + rgb + depth losses only)"""
+        """fast path: the whole step as one fixed kernel sequence / CUDA graph.  Returns (graph step, device weights) or None for
+        configurations that take the general path (learnable focal, pose-smoothness terms, no render terms, foreign optimizers)."""
         if not self.fused_adam or self.optimizer_focal or self.pose_param_net is None or self.distortion_net is None:
             return None
         if self.optimizer_pose is None or self.optimizer_distortion is None:
@@ -436,23 +516,65 @@ class Trainer(object):
         names = ['rgb_weight', 'depth_weight', 'pc_weight', 'rgb_s_weight', 'depth_consistency_weight', 'weight_dist_2nd_loss',
                  'weight_dist_1st_loss']
         wts = {n: self.anneal(getattr(self, n)[0], getattr(self, n)[1], scheduling_start, self.annealing_epochs, epoch) for n in names}
-        if any(wts[n] != 0.0 for n in names[2:]) or (wts['rgb_weight'] == 0.0 and wts['depth_weight'] == 0.0):
+        if any(wts[n] != 0.0 for n in names[4:]) or (wts['rgb_weight'] == 0.0 and wts['depth_weight'] == 0.0):
             return None
+        use_ref = wts['pc_weight'] != 0.0 or wts['rgb_s_weight'] != 0.0
+        if use_ref:
+            self._check_ref_stage_cfg()
+            if data.get('img.ref_imgs') is None:
+                return None
         rgb_l2 = not (epoch < self.annealing_epochs + scheduling_start)
         img = data.get('img'); dpt = data.get('img.dpt')
         _, _, h, w = img.shape
         hd, wd = dpt.shape[-2:]
-        key = (h, w, hd, wd, float(wts['rgb_weight']), float(wts['depth_weight']), bool(rgb_l2))
+        key = (h, w, hd, wd, bool(rgb_l2), bool(use_ref))
         gs = self._gsteps.get(key)
         if gs is None:
-            gs = _GraphStep(self, h, w, hd, wd, wts['rgb_weight'], wts['depth_weight'], rgb_l2)
+            gs = _GraphStep(self, h, w, hd, wd, rgb_l2, use_ref)
             if not gs.eligible_optimizers():
                 self._gsteps[key] = False
                 return None
             self._gsteps[key] = gs
         if gs is False:
             return None
-        return gs
+        return gs, [float(wts['rgb_weight']), float(wts['depth_weight']), float(wts['pc_weight']), float(wts['rgb_s_weight'])]
+
+    def graph_kernel_nodes(self):
+        """{kernels, memcpy, memset, other} node counts of the captured step graph(s) (needs Trainer(keep_graph=True)); None if no
+        graph has been captured or the CUDA runtime bindings are unavailable"""
+        try:
+            from cuda.bindings import runtime as rt
+        except Exception:
+            return None
+        tot = {"kernels": 0, "memcpy": 0, "memset": 0, "other": 0}
+        found = False
+        for gs in self._gsteps.values():
+            if not gs or gs.graph is None:
+                continue
+            for gr in (gs.graph, getattr(gs, 'graph_b', None)):
+                if gr is None:
+                    continue
+                try:
+                    raw = gr.raw_cuda_graph()
+                    err, _, n = rt.cudaGraphGetNodes(raw, 0)
+                    err, nodes, n = rt.cudaGraphGetNodes(raw, n)
+                    for nd in nodes[:n]:
+                        err, ty = rt.cudaGraphNodeGetType(nd)
+                        k = {rt.cudaGraphNodeType.cudaGraphNodeTypeKernel: "kernels", rt.cudaGraphNodeType.cudaGraphNodeTypeMemcpy: "memcpy",
+                             rt.cudaGraphNodeType.cudaGraphNodeTypeMemset: "memset"}.get(ty, "other")
+                        tot[k] += 1
+                    found = True
+                except Exception:
+                    return None
+        return tot if found else None
+
+    def _check_ref_stage_cfg(self):
+        """the fused reference-image stage (nnb_refstage) covers the reference's defaults"""
+        if not self.detach_ref_img:
+            raise NotImplementedError("training.detach_ref_img=False (gradients into the reference view) is not fused; the default is True "
+                                      "(configs/default.yaml:117)")
+        if self.match_method != 'dense':
+            raise NotImplementedError("training.match_method=%r: only 'dense' (configs/default.yaml) is fused" % (self.match_method,))
 
     # ------------------------------------------------------------------------------------
     def process_data_dict(self, data, keep_pinned=False):
@@ -583,31 +705,71 @@ class Trainer(object):
                 if shift_input.requires_grad:
                     outs.append(shift_input); gouts.append(g_ss[1:2].reshape(shift_input.shape))
                 if outs:
-                    torch.autograd.backward(outs, gouts, retain_graph=use_ref_imgs)
+                    torch.autograd.backward(outs, gouts, retain_graph=use_ref_imgs)   # the distortion module is differentiated again by the reference-image stage
                 if g_cam is not None and fxfy.requires_grad:
                     camera_mat.backward(g_cam.view(1, 4, 4), retain_graph=use_ref_imgs)
 
         ref_terms = {}
         if use_ref_imgs:
-            ref_loss, ref_terms = self._reference_stage(img, ref_img, depth_input, depth_ref, img_idx, ref_idx, camera_mat,
-                                                        scale_input, shift_input, weights, it, out_render_path)
+            # reference-image stage (training.py:280-365): point-cloud + warped-RGB terms, forward + adjoint in ONE library call
+            self._check_ref_stage_cfg()
+            _, _, h_depth, w_depth = depth_input.shape
+            init = None if pose.init_c2w is None else pose.init_c2w.detach()
+            c2w_cur = torch.empty(4, 4, device=device); c2w_ref = torch.empty(4, 4, device=device)
+            ops.pose_fwd_raw(pose.r.detach(), pose.t.detach(), init, img_idx, c2w_cur)
+            ops.pose_fwd_raw(pose.r.detach(), pose.t.detach(), init, ref_idx, c2w_ref)                  # detached (training.py:288-292)
+            if self.distortion_net is not None:
+                s_ref, h_ref = self.distortion_net(ref_idx)
+            else:
+                s_ref = torch.ones(1, device=device); h_ref = torch.zeros(1, device=device)
+            dist_cur = torch.cat([scale_dev, shift_dev]); dist_ref = torch.stack([s_ref.detach().reshape(()), h_ref.detach().reshape(())]).float()
+            rs_losses = torch.zeros(2, device=device); rs_total = torch.zeros(1, device=device)
+            g_c2w_rs = torch.zeros(4, 4, device=device) if backward else None
+            g_ss_rs = torch.zeros(2, device=device) if backward else None
+            g_kxy_rs = torch.zeros(2, device=device) if (backward and fxfy is not None) else None
+            ops.refstage_raw(c2w_cur, dist_cur, c2w_ref, dist_ref, depth_input.detach().reshape(h_depth, w_depth).contiguous(),
+                             depth_ref.detach().reshape(h_depth, w_depth).contiguous(), H=h, W=w, img_cur=ops._f32c(img[0]), img_ref=ops._f32c(ref_img[0]),
+                             is_last=(img_idx == V - 1), cam=cam_dev, nearest_limit=self.nearest_limit, pc_ratio=self.pc_ratio,
+                             scale_pcs=self.scale_pcs, detach_rgbs_scale=self.detach_rgbs_scale, shift_first=self.shift_first,
+                             w_pc=weights['pc_weight'], w_rgb_s=weights['rgb_s_weight'], losses=rs_losses, g_c2w=g_c2w_rs, g_dist=g_ss_rs,
+                             g_kxy=g_kxy_rs, loss_total=rs_total, grad_scale=grad_scale)
+            if weights['pc_weight'] != 0.0: ref_terms['loss_pc'] = rs_losses[0]
+            if weights['rgb_s_weight'] != 0.0: ref_terms['loss_rgb_s'] = rs_losses[1]
+            loss_total = loss_total + rs_total[0]
             if backward:
-                (ref_loss * grad_scale).backward()
-            loss_total = loss_total + ref_loss.detach()
+                ops.pose_bwd_raw(pose.r.detach(), pose.t.detach(), init, img_idx, g_c2w_rs,
+                                 gv['r'] if pose.r.requires_grad else None, gv['t'] if pose.t.requires_grad else None)
+                outs, gouts = [], []
+                if scale_input.requires_grad:
+                    outs.append(scale_input); gouts.append(g_ss_rs[0:1].reshape(scale_input.shape))
+                if shift_input.requires_grad:
+                    outs.append(shift_input); gouts.append(g_ss_rs[1:2].reshape(shift_input.shape))
+                if outs:
+                    torch.autograd.backward(outs, gouts)
+                if g_kxy_rs is not None and fxfy.requires_grad:
+                    fxfy.backward(torch.stack([g_kxy_rs[0], -g_kxy_rs[1]]))          # camera_mat = diag(fx, -fy, -1, 1)
 
-        # ---- data-parallel: ONE all-reduce of [grads | loss scalars] -----------------------
-        if backward and self.world > 1:
-            torch.distributed.all_reduce(gbuf, group=self.dp_group)
-        zero = torch.zeros((), device=device)
-        loss_dict = {'loss': losses4[0] + loss_total, 'loss_rgb': losses4[1], 'loss_depth': losses4[2], 'l2_mean': losses4[3],
-                     'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': ref_terms.get('loss_pc', zero),
-                     'loss_rgb_s': ref_terms.get('loss_rgb_s', zero), 'loss_depth_consistency': zero}
+        # pose-smoothness terms (losses.py:103-112, weight 0 by default): every rank holds the same t, so each contributes
+        # 1/world of the gradient BEFORE the all-reduce sums the ranks
+        dist_terms = None
         if weights['weight_dist_2nd_loss'] != 0.0 or weights['weight_dist_1st_loss'] != 0.0:
             d1, d2 = self.loss.get_weight_dist_loss(pose.get_t())
             extra = weights['weight_dist_1st_loss'] * d1 + weights['weight_dist_2nd_loss'] * d2
             if backward: (extra * grad_scale).backward()
-            loss_dict['loss_dist_1st'], loss_dict['loss_dist_2nd'] = d1.detach(), d2.detach()
-            loss_dict['loss'] = loss_dict['loss'] + extra.detach()
+            dist_terms = (d1.detach(), d2.detach(), extra.detach())
+        # ---- data-parallel: ONE all-reduce of [grads | loss scalars] -----------------------
+        if backward and self.world > 1:
+            torch.distributed.all_reduce(gbuf, group=self.dp_group)
+            if self.optimizer_focal:         # focal gradients (2 floats, off by default) live outside the flat buffer
+                for p_ in self.focal_net.parameters():
+                    if p_.grad is not None: torch.distributed.all_reduce(p_.grad, group=self.dp_group)
+        zero = torch.zeros((), device=device)
+        loss_dict = {'loss': losses4[0] + loss_total, 'loss_rgb': losses4[1], 'loss_depth': losses4[2], 'l2_mean': losses4[3],
+                     'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': ref_terms.get('loss_pc', zero),
+                     'loss_rgb_s': ref_terms.get('loss_rgb_s', zero), 'loss_depth_consistency': zero}
+        if dist_terms is not None:
+            loss_dict['loss_dist_1st'], loss_dict['loss_dist_2nd'] = dist_terms[0], dist_terms[1]
+            loss_dict['loss'] = loss_dict['loss'] + dist_terms[2]
         if self.optimizer_focal:
             loss_dict['focalx'] = fxfy[0] / camera_mat_gt[0, 0, 0]
             loss_dict['focaly'] = fxfy[1] / camera_mat_gt[0, 1, 1]
@@ -616,91 +778,6 @@ class Trainer(object):
         if call is not None and not backward:
             call.release()
         return loss_dict
-
-    # ------------------------------------------------------------------------------------
-    def _reference_stage(self, img, ref_img, depth_input, depth_ref, img_idx, ref_idx, camera_mat, scale_input, shift_input,
-                         weights, it, out_render_path):
-        """training.py:280-365 (point-cloud + warped-RGB terms) with autograd over small tensors."""
-        device = self.device
-        pose = self.pose_param_net
-        num_cams = pose.num_cams
-        nl = self.nearest_limit
-        if self.native_ref_stage:
-            if self.shift_first or not self.detach_ref_img:
-                raise NotImplementedError("native_ref_stage covers the default shift_first=False, detach_ref_img=True")
-            if self.distortion_net is not None:
-                s_ref, h_ref = self.distortion_net(ref_idx)
-            else:
-                s_ref = torch.ones(1, device=device); h_ref = torch.zeros(1, device=device)
-            dist_cur = torch.stack([scale_input.reshape(()), shift_input.reshape(())])
-            dist_ref = torch.stack([s_ref.reshape(()), h_ref.reshape(())]).detach()
-            cm = camera_mat.reshape(4, 4)
-            total, losses = ops.refstage(pose(img_idx), dist_cur, pose(ref_idx).detach(), dist_ref, img[0], ref_img[0], depth_input[0, 0],
-                                         depth_ref[0, 0], img_idx == num_cams - 1, float(cm[0, 0]), float(cm[1, 1]), nearest_limit=nl,
-                                         pc_ratio=self.pc_ratio, scale_pcs=self.scale_pcs, detach_rgbs_scale=self.detach_rgbs_scale,
-                                         w_pc=weights['pc_weight'], w_rgb_s=weights['rgb_s_weight'])
-            terms = {}
-            if weights['pc_weight'] != 0.0: terms['loss_pc'] = losses[0]
-            if weights['rgb_s_weight'] != 0.0: terms['loss_rgb_s'] = losses[1]
-            return total, terms
-        _, _, h_depth, w_depth = depth_input.shape
-        c2w = pose(img_idx)                                         # differentiable (nnb_pose_fwd/bwd)
-        if self.shift_first: d_in = (depth_input + shift_input) * scale_input       # training.py:241-245
-        else: d_in = depth_input * scale_input + shift_input
-        c2w_ref = pose(ref_idx)
-        if self.distortion_net is not None:
-            scale_ref, shift_ref = self.distortion_net(ref_idx)
-        else:
-            scale_ref = torch.ones(1, device=device); shift_ref = torch.zeros(1, device=device)
-        d_ref = scale_ref * (depth_ref + shift_ref) if self.shift_first else scale_ref * depth_ref + shift_ref
-        if self.detach_ref_img:
-            c2w_ref = c2w_ref.detach(); scale_ref = scale_ref.detach(); d_ref = d_ref.detach()
-        world_mat = torch.linalg.inv(c2w).unsqueeze(0)
-        ref_Rt = torch.linalg.inv(c2w_ref).unsqueeze(0)
-        if img_idx < (num_cams - 1):                                # training.py:296-313
-            d1, d2, img1, img2 = d_in, d_ref, img, ref_img
-            Rt_rel_12 = ref_Rt @ torch.linalg.inv(world_mat)
-            scale2 = scale_ref
-        else:
-            d1, d2, img1, img2 = d_ref, d_in, ref_img, img
-            Rt_rel_12 = world_mat @ torch.linalg.inv(ref_Rt)
-            scale2 = scale_input
-        R_rel_12 = Rt_rel_12[:, :3, :3]; t_rel_12 = Rt_rel_12[:, :3, 3]
-        ratio = self.pc_ratio
-        res = (int(h_depth / ratio), int(w_depth / ratio))
-        pixel_locations, p_pc = self._pixels(res, device)
-        d1 = torch.clamp(F.interpolate(d1, res, mode='nearest'), min=nl)    # training.py:318-321
-        d2 = torch.clamp(F.interpolate(d2, res, mode='nearest'), min=nl)
-        cm = camera_mat.reshape(4, 4)
-        kx, ky = cm[0, 0], cm[1, 1]
-
-        def backproject(d):                                         # transform_to_world with identity pose (common.py:112-160)
-            dd = d.reshape(1, -1)
-            return torch.stack([p_pc[..., 0] * dd / kx, p_pc[..., 1] * dd / ky, -dd], dim=-1)
-        pc1 = backproject(d1); pc2 = backproject(d2)
-        terms = {}
-        total = torch.zeros((), device=device)
-        if weights['rgb_s_weight'] != 0.0:
-            i1 = F.interpolate(img1, res, mode='bilinear'); i2 = F.interpolate(img2, res, mode='bilinear')
-            grid = p_pc.unsqueeze(1)
-            rgb_pc1 = F.grid_sample(i1, grid, mode='bilinear', align_corners=True).squeeze(2).permute(0, 2, 1)
-            src = pc1.detach().clone() if self.detach_rgbs_scale else pc1
-            pc1_rot = src @ R_rel_12.transpose(1, 2) + t_rel_12
-            invalid = (-pc1_rot[:, :, 2:] < nl).expand_as(pc1_rot)                      # training.py:334-335
-            pc1_rot = torch.where(invalid, torch.full_like(pc1_rot, nl), pc1_rot)
-            xy = torch.stack([kx * pc1_rot[..., 0], ky * pc1_rot[..., 1]], -1) / (-pc1_rot[..., 2:])   # common.py:436-457
-            valid = (xy.abs().max(dim=-1)[0] <= 1).unsqueeze(-1)
-            rgb_proj = F.grid_sample(i2, xy.unsqueeze(1), mode='bilinear', align_corners=True).squeeze(2).permute(0, 2, 1)
-            l = self.loss.get_rgb_s_loss(rgb_pc1, rgb_proj, valid)
-            terms['loss_rgb_s'] = l.detach(); total = total + weights['rgb_s_weight'] * l
-        if weights['pc_weight'] != 0.0:
-            X = pc1 @ R_rel_12.transpose(1, 2) + t_rel_12                             # training.py:356
-            Y = pc2
-            if self.scale_pcs:
-                X = X / scale2; Y = Y / scale2
-            l = self.loss.get_pc_loss(X, Y)
-            terms['loss_pc'] = l.detach(); total = total + weights['pc_weight'] * l
-        return total, terms
 
     # ------------------------------------------------------------------------------------
     def render_visdata(self, data, resolution, it, out_render_path):

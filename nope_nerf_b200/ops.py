@@ -244,11 +244,11 @@ class _ChamferFn(torch.autograd.Function):
     def forward(ctx, X, Y):
         X = _f32c(X); Y = _f32c(Y)
         P, Q = X.shape[0], Y.shape[0]
-        ixy = torch.empty(P, dtype=torch.int32, device=X.device); iyx = torch.empty(Q, dtype=torch.int32, device=X.device)
+        keys = torch.empty(P + Q, dtype=torch.int64, device=X.device)
         loss = torch.zeros(1, device=X.device)
         need = X.requires_grad or Y.requires_grad
         gX = torch.zeros_like(X) if need else None; gY = torch.zeros_like(Y) if need else None
-        L.check(L.lib.nnb_chamfer(L.ptr(X), P, L.ptr(Y), Q, L.ptr(ixy), L.ptr(iyx), L.ptr(loss), 1.0, L.ptr(gX), L.ptr(gY),
+        L.check(L.lib.nnb_chamfer(L.ptr(X), P, L.ptr(Y), Q, L.ptr(keys), None, None, L.ptr(loss), 1.0, L.ptr(gX), L.ptr(gY),
                                   _stream()), "nnb_chamfer")
         ctx.save_for_backward(gX if need else X.new_empty(0), gY if need else X.new_empty(0))
         return loss[0]
@@ -265,44 +265,84 @@ def chamfer(X, Y):
     return _ChamferFn.apply(X, Y)
 
 
+_rs_ws = {}
+
+
+def refstage_raw(c2w_cur, dist_cur, c2w_ref, dist_ref, dpt_cur, dpt_ref, *, H, W, img_cur=None, img_ref=None, img_pp=None, is_last=False,
+                 kx=0.0, ky=0.0, cam=None, cam_idx_dev=None, num_cams=0, weights_dev=None, nearest_limit=0.01, pc_ratio=4, scale_pcs=True,
+                 detach_rgbs_scale=False, shift_first=False, w_pc=1.0, w_rgb_s=1.0, losses=None, g_c2w=None, g_dist=None, g_kxy=None,
+                 loss_total=None, grad_scale=1.0, workspace=None):
+    """nnb_refstage: the reference-image stage of Trainer.compute_loss (model/training.py:280-365), forward + adjoint in one call.
+    All tensor arguments are device tensors (frames may be page-locked host tensors); g_* / loss_total ACCUMULATE."""
+    _need_cuda(c2w_cur, "c2w_cur")
+    for n_, t_ in (("img_cur", img_cur), ("img_ref", img_ref)):
+        _need_cuda(t_, n_, allow_pinned=True)
+    dev = c2w_cur.device
+    hd, wd = int(dpt_cur.shape[-2]), int(dpt_cur.shape[-1])
+    nbytes = L.lib.nnb_refstage_workspace_bytes(hd, wd, int(pc_ratio))
+    if nbytes == 0:
+        raise ValueError("reference-image stage: DPT map %dx%d too small for pc_ratio %d" % (hd, wd, pc_ratio))
+    if workspace is None:
+        key = (nbytes, dev.index)
+        workspace = _rs_ws.get(key)
+        if workspace is None:
+            workspace = _rs_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if losses is None:
+        losses = torch.zeros(2, device=dev)
+    a = L.RefStageArgs()
+    a.img_cur, a.img_ref, a.dpt_cur, a.dpt_ref = L.ptr(img_cur), L.ptr(img_ref), L.ptr(dpt_cur), L.ptr(dpt_ref)
+    a.c2w_cur, a.c2w_ref, a.dist_cur, a.dist_ref = L.ptr(c2w_cur), L.ptr(c2w_ref), L.ptr(dist_cur), L.ptr(dist_ref)
+    a.H, a.W, a.h_d, a.w_d, a.pc_ratio, a.is_last = int(H), int(W), hd, wd, int(pc_ratio), int(bool(is_last))
+    a.flags = (1 if scale_pcs else 0) | (2 if detach_rgbs_scale else 0) | (4 if shift_first else 0)
+    a.kx, a.ky, a.nearest_limit, a.w_pc, a.w_rgb_s = float(kx), float(ky), float(nearest_limit), float(w_pc), float(w_rgb_s)
+    a.losses, a.g_c2w, a.g_dist = L.ptr(losses), L.ptr(g_c2w), L.ptr(g_dist)
+    a.workspace, a.workspace_bytes = L.ptr(workspace), workspace.numel()
+    a.img_pp, a.cam, a.cam_idx_dev, a.num_cams, a.weights_dev = L.ptr(img_pp), L.ptr(cam), L.ptr(cam_idx_dev), int(num_cams), L.ptr(weights_dev)
+    a.g_kxy, a.loss_total, a.grad_scale = L.ptr(g_kxy), L.ptr(loss_total), float(grad_scale)
+    L.check(L.lib.nnb_refstage(C.byref(a), _stream()), "nnb_refstage")
+    return losses
+
+
 class _RefStageFn(torch.autograd.Function):
     """w_pc * loss_pc + w_rgb_s * loss_rgb_s of the reference-image stage (model/training.py:280-365) as a function of the current
-    view's pose matrix and effective distortion {scale, shift}; forward and adjoint come out of ONE library call (nnb_refstage)."""
+    view's pose matrix, effective distortion {scale, shift} and (kx, ky); forward and adjoint come out of ONE library call."""
 
     @staticmethod
-    def forward(ctx, c2w_cur, dist_cur, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, kx, ky, nearest_limit, pc_ratio,
-                scale_pcs, detach_rgbs_scale, w_pc, w_rgb_s):
+    def forward(ctx, c2w_cur, dist_cur, kxy, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, nearest_limit, pc_ratio,
+                scale_pcs, detach_rgbs_scale, shift_first, w_pc, w_rgb_s):
         dev = c2w_cur.device
-        c2w_cur = _f32c(c2w_cur.detach()); dist_cur = _f32c(dist_cur.detach()); c2w_ref = _f32c(c2w_ref.detach()); dist_ref = _f32c(dist_ref.detach())
-        img_cur = _f32c(img_cur); img_ref = _f32c(img_ref); dpt_cur = _f32c(dpt_cur); dpt_ref = _f32c(dpt_ref)
-        H, W = img_cur.shape[-2:]; hd, wd = dpt_cur.shape[-2:]
-        nbytes = L.lib.nnb_refstage_workspace_bytes(int(hd), int(wd), int(pc_ratio))
-        if nbytes == 0:
-            raise ValueError("reference-image stage: DPT map %dx%d too small for pc_ratio %d" % (hd, wd, pc_ratio))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        losses = torch.zeros(2, device=dev); g_c2w = torch.zeros(4, 4, device=dev); g_dist = torch.zeros(2, device=dev)
-        a = L.RefStageArgs(L.ptr(img_cur), L.ptr(img_ref), L.ptr(dpt_cur), L.ptr(dpt_ref), L.ptr(c2w_cur), L.ptr(c2w_ref), L.ptr(dist_cur),
-                           L.ptr(dist_ref), int(H), int(W), int(hd), int(wd), int(pc_ratio), int(bool(is_last)),
-                           (1 if scale_pcs else 0) | (2 if detach_rgbs_scale else 0), float(kx), float(ky), float(nearest_limit), float(w_pc),
-                           float(w_rgb_s), L.ptr(losses), L.ptr(g_c2w), L.ptr(g_dist), L.ptr(ws), nbytes)
-        L.check(L.lib.nnb_refstage(a, _stream()), "nnb_refstage")
-        ctx.save_for_backward(g_c2w, g_dist)
+        f = lambda t: _f32c(t.detach())
+        H, W = img_cur.shape[-2:]
+        g_c2w = torch.zeros(4, 4, device=dev); g_dist = torch.zeros(2, device=dev); g_kxy = torch.zeros(2, device=dev)
+        kx, ky = (float(v) for v in kxy.detach().cpu())
+        losses = refstage_raw(f(c2w_cur), f(dist_cur), f(c2w_ref), f(dist_ref), _f32c(dpt_cur), _f32c(dpt_ref), H=H, W=W, img_cur=_f32c(img_cur),
+                              img_ref=_f32c(img_ref), is_last=is_last, kx=kx, ky=ky, nearest_limit=nearest_limit, pc_ratio=pc_ratio,
+                              scale_pcs=scale_pcs, detach_rgbs_scale=detach_rgbs_scale, shift_first=shift_first, w_pc=w_pc, w_rgb_s=w_rgb_s,
+                              g_c2w=g_c2w, g_dist=g_dist, g_kxy=g_kxy, workspace=torch.empty(
+                                  L.lib.nnb_refstage_workspace_bytes(int(dpt_cur.shape[-2]), int(dpt_cur.shape[-1]), int(pc_ratio)) or 1,
+                                  dtype=torch.uint8, device=dev))
+        ctx.save_for_backward(g_c2w, g_dist, g_kxy)
         ctx.mark_non_differentiable(losses)
         return float(w_pc) * losses[0] + float(w_rgb_s) * losses[1], losses
 
     @staticmethod
     def backward(ctx, g, _g_losses):
-        g_c2w, g_dist = ctx.saved_tensors
-        return (g_c2w * g if ctx.needs_input_grad[0] else None, g_dist * g if ctx.needs_input_grad[1] else None) + (None,) * 15
+        g_c2w, g_dist, g_kxy = ctx.saved_tensors
+        return (g_c2w * g if ctx.needs_input_grad[0] else None, g_dist * g if ctx.needs_input_grad[1] else None,
+                g_kxy * g if ctx.needs_input_grad[2] else None) + (None,) * 14
 
 
 def refstage(c2w_cur, dist_cur, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, kx, ky, nearest_limit=0.01, pc_ratio=4,
-             scale_pcs=True, detach_rgbs_scale=False, w_pc=1.0, w_rgb_s=1.0):
-    """(total, losses[2] = {loss_pc, loss_rgb_s}); total is differentiable w.r.t. c2w_cur (4,4) and dist_cur = [scale_eff, shift].
-    EXPERIMENTAL in round 1 (see include/nope_nerf_b200.h)."""
+             scale_pcs=True, detach_rgbs_scale=False, shift_first=False, w_pc=1.0, w_rgb_s=1.0):
+    """(total, losses[2] = {loss_pc, loss_rgb_s}); total is differentiable w.r.t. c2w_cur (4,4), dist_cur = [scale_eff, shift] and, when
+    kx / ky are tensors, the intrinsics (autograd wrapper over refstage_raw; the Trainer calls refstage_raw directly)."""
     _need_cuda(c2w_cur, "c2w_cur")
-    return _RefStageFn.apply(c2w_cur, dist_cur, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, kx, ky, nearest_limit, pc_ratio,
-                             scale_pcs, detach_rgbs_scale, w_pc, w_rgb_s)
+    if isinstance(kx, torch.Tensor) or isinstance(ky, torch.Tensor):
+        kxy = torch.stack([torch.as_tensor(kx, device=c2w_cur.device).reshape(()), torch.as_tensor(ky, device=c2w_cur.device).reshape(())])
+    else:
+        kxy = torch.tensor([float(kx), float(ky)], device=c2w_cur.device)
+    return _RefStageFn.apply(c2w_cur, dist_cur, kxy, c2w_ref, dist_ref, img_cur, img_ref, dpt_cur, dpt_ref, is_last, nearest_limit, pc_ratio,
+                             scale_pcs, detach_rgbs_scale, shift_first, w_pc, w_rgb_s)
 
 
 def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -339,10 +379,11 @@ def counter_incr(counters):
     L.check(L.lib.nnb_counter_incr(L.ptr(counters), counters.numel(), _stream()), "nnb_counter_incr")
 
 
-def loss_rgb_depth_indirect(rgb, depth_pred, depth_gt, mask, w_rgb, w_depth, rgb_l2, img_pp, ray_idx, HW, out, g_rgb, g_dp, g_dg, grad_scale=1.0):
+def loss_rgb_depth_indirect(rgb, depth_pred, depth_gt, mask, w_rgb, w_depth, rgb_l2, img_pp, ray_idx, HW, out, g_rgb, g_dp, g_dg, grad_scale=1.0,
+                            w_dev=None):
     L.check(L.lib.nnb_loss_rgb_depth_indirect(L.ptr(rgb), L.ptr(img_pp), L.ptr(ray_idx), int(HW), L.ptr(depth_pred), L.ptr(depth_gt), L.ptr(mask),
                                               rgb.shape[0], float(w_rgb), float(w_depth), int(bool(rgb_l2)), float(grad_scale), L.ptr(out),
-                                              L.ptr(g_rgb), L.ptr(g_dp), L.ptr(g_dg), _stream()), "nnb_loss_rgb_depth_indirect")
+                                              L.ptr(g_rgb), L.ptr(g_dp), L.ptr(g_dg), L.ptr(w_dev), _stream()), "nnb_loss_rgb_depth_indirect")
 
 
 def sample_pixels(hw, n, device):

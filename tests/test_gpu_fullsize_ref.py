@@ -1,0 +1,193 @@
+"""Full-size parity against the LIVE reference on cuda (oracle/_ref = an unmodified copy of the reference tree, made by
+tools/vendor_ref.py; it ships to the GPU box like the built .so).  BASELINE.json's configs at their REAL sizes:
+
+  C2  1080x1920, DPT 384x672, V=200, 1024 rays x 128 samples, uniform + jitter, rgb L1 + depth L1            (+ full loss set)
+  C3  756x1008,  DPT 384x512, V=20,  1024 rays x 128 samples, NDC + dist_alpha, depth loss on 1 - 1/d
+  C5  1080x1920, 4096 rays x 128 samples (one rank's view of the 8-view batch), full loss set
+
+Both sides start from the same parameters (the reference's own torch init under a fixed seed), see the same frame pair, the
+same `ray_idx` (torch.randperm is patched to return a stored draw) and the same jitter (torch.rand likewise), and run ONE
+Trainer.train_step.  Compared: every loss scalar, the pose / distortion / MLP gradients the step leaves in .grad, and the rendered
+rgb / depth of a forward-only call.  The gradient gate is max(1e-4, 3 x envelope), envelope = |reference fp32 - reference fp64|
+(the reference itself re-run in float64 on the same inputs = its own rounding, dominated by ReLU-gate switches, see
+tests/test_oracle_golden.py::test_render_gate_matched_and_kxy)."""
+import os
+import sys
+import numpy as np
+import pytest
+import torch
+
+from _util import ROOT
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as RH  # noqa: E402
+
+if not RH.available():
+    pytest.skip("oracle/_ref missing (run tools/vendor_ref.py in the build container)", allow_module_level=True)
+
+REPORT = {}
+
+
+def _report(key, **vals):
+    import json
+    REPORT[key] = {k: float(v) for k, v in vals.items()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_fullsize_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def rel(a, b):
+    a = a.detach().double().reshape(-1); b = b.detach().double().reshape(-1)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a = a.detach().double().reshape(-1); b = b.detach().double().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+CASES = {
+    "C2_render": dict(H=1080, W=1920, hd=384, wd=672, V=200, N=1024, S=128, over={"training.pc_weight": [0.0, 0.0], "training.rgb_s_weight": [0.0, 0.0]}),
+    "C2_full": dict(H=1080, W=1920, hd=384, wd=672, V=200, N=1024, S=128, over={}),
+    "C3_ndc": dict(H=756, W=1008, hd=384, wd=512, V=20, N=1024, S=128,
+                   over={"rendering.sample_option": "ndc", "rendering.dist_alpha": True, "rendering.depth_range": [0.0, 1.0],
+                         "training.pc_weight": [0.0, 0.0], "training.rgb_s_weight": [0.0, 0.0]}),
+    "C5_full": dict(H=1080, W=1920, hd=384, wd=672, V=200, N=4096, S=128, over={}),
+}
+
+
+def _cfg(c):
+    cfg = RH.load_default_cfg()
+    RH.set_cfg(cfg, c["over"])
+    cfg["training"]["n_training_points"] = c["N"]; cfg["rendering"]["num_points"] = c["S"]
+    cfg["training"]["vis_reprojection_every"] = 10 ** 9
+    return cfg
+
+
+def _data(c, idx, seed):
+    g = torch.Generator().manual_seed(seed)
+    H, W, hd, wd = c["H"], c["W"], c["hd"], c["wd"]
+    fx = 0.6 * W
+    cam = torch.tensor([[2 * fx / W, 0, 0, 0], [0, -2 * fx / H, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], dtype=torch.float32)[None]
+    # smooth frames / depth maps (low-res noise, bilinearly upsampled) so that the warped-RGB term sees image structure
+    up = lambda t, size: torch.nn.functional.interpolate(t, size, mode="bilinear", align_corners=False)
+    img = up(torch.rand(1, 3, 27, 48, generator=g), (H, W)).contiguous()
+    ref = up(torch.rand(1, 3, 27, 48, generator=g), (H, W)).contiguous()
+    dpt = (up(torch.rand(1, 1, 12, 21, generator=g), (hd, wd))[0] * 3.0 + 2.0).contiguous()
+    rdpt = (dpt * (1 + 0.05 * up(torch.rand(1, 1, 6, 8, generator=g), (hd, wd))[0])).contiguous()
+    return {"img": img, "img.idx": torch.tensor([idx]), "img.dpt": dpt, "img.camera_mat": cam, "img.scale_mat": torch.eye(4)[None],
+            "img.ref_imgs": ref, "img.ref_dpts": rdpt, "img.ref_idxs": torch.tensor([idx + 1])}
+
+
+def _ours(cfg, V, state, use_cuda_graph=False):
+    import nope_nerf_b200.model as mdl
+    dev = torch.device("cuda")
+    net = mdl.OfficialStaticNerf(cfg)
+    net.load_state_dict({k: v.clone() for k, v in state["net"].items()})
+    rend = mdl.Renderer(net, cfg["rendering"], device=dev)
+    model = mdl.get_model(rend, cfg, device=dev)
+    pose = mdl.LearnPose(V, True, True, cfg).to(dev); dist = mdl.Learn_Distortion(V, True, True, cfg).to(dev)
+    with torch.no_grad():
+        pose.r.copy_(state["r"]); pose.t.copy_(state["t"]); dist.global_scales.copy_(state["scales"]); dist.global_shifts.copy_(state["shifts"])
+    tr = cfg["training"]
+    opt = torch.optim.Adam(model.parameters(), lr=tr["learning_rate"]); opt_p = torch.optim.Adam(pose.parameters(), lr=tr["pose_lr"])
+    opt_d = torch.optim.Adam(dist.parameters(), lr=tr["distortion_lr"])
+    trainer = mdl.Trainer(model, opt, tr, device=dev, optimizer_pose=opt_p, pose_param_net=pose, optimizer_distortion=opt_d, distortion_net=dist,
+                          use_cuda_graph=use_cuda_graph)
+    return trainer, net, pose, dist, model
+
+
+def _init_state(rig, V, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        rig.pose.r.copy_((torch.randn(V, 3, generator=g) * 0.05).cuda()); rig.pose.t.copy_((torch.randn(V, 3, generator=g) * 0.05).cuda())
+        rig.dist.global_scales.copy_((1 + 0.1 * (torch.rand(V, 1, generator=g) - 0.5)).cuda())
+        rig.dist.global_shifts.copy_((0.1 * (torch.rand(V, 1, generator=g) - 0.5)).cuda())
+    return rig.state()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("eng", ["tc", "simt"])
+def test_train_step_vs_live_reference(name, eng, monkeypatch):
+    from nope_nerf_b200 import ops
+    if eng == "simt" and name != "C2_render":
+        pytest.skip("exact-fp32 engine: one full-size case is enough (6 ms kernels)")
+    ops.set_default_engine(eng)
+    c = CASES[name]; cfg = _cfg(c); V = c["V"]; idx = 7
+    torch.manual_seed(1234)
+    rig = RH.RefRig(cfg, V, "cuda")
+    state = _init_state(rig, V, 99)
+    data = _data(c, idx, 5)
+    H, W, N, S = c["H"], c["W"], c["N"], c["S"]
+    g = torch.Generator().manual_seed(77)
+    ray_idx = torch.randperm(H * W, generator=g)[:N].cuda(); noise = torch.rand(1, N, S, generator=g).cuda()
+    real_randperm, real_rand = torch.randperm, torch.rand
+    monkeypatch.setattr(torch, "randperm", lambda n, *a, **k: ray_idx if n == H * W else real_randperm(n, *a, **k))
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: noise.to(torch.get_default_dtype()) if tuple(a) == (1, N, S) else real_rand(*a, **k))
+    # ---- reference fp32 (live, cuda) ----
+    ld_ref = rig.train_step(data)
+    gref = dict(r=rig.pose.r.grad.clone(), t=rig.pose.t.grad.clone(), scales=rig.dist.global_scales.grad.clone() if rig.dist.global_scales.grad is not None else torch.zeros(V, 1).cuda(),
+                shifts=rig.dist.global_shifts.grad.clone(), params=torch.cat([p.grad.reshape(-1) for p in rig.net.parameters()]))
+    # ---- reference fp64 (its own rounding envelope): the same unmodified code under float64 defaults ----
+    with RH.fp64_mode():
+        rig64 = RH.RefRig(cfg, V, "cuda", state=state)
+        data64 = {k: (v.double() if v.is_floating_point() else v) for k, v in data.items()}
+        rig64.train_step(data64)
+        g64 = dict(r=rig64.pose.r.grad, t=rig64.pose.t.grad, shifts=rig64.dist.global_shifts.grad,
+                   scales=rig64.dist.global_scales.grad if rig64.dist.global_scales.grad is not None else torch.zeros(V, 1).cuda(),
+                   params=torch.cat([p.grad.reshape(-1) for p in rig64.net.parameters()]))
+        env = {k: rel(gref[k], g64[k]) for k in gref}
+        del rig64
+    # ---- ours ----
+    trainer, net, pose, dist, _ = _ours(cfg, V, state)
+    ld = trainer.train_step(data, it=1, epoch=0, scheduling_start=10000, render_path="/tmp")
+    torch.cuda.synchronize()
+    gours = dict(r=pose.r.grad, t=pose.t.grad, scales=dist.global_scales.grad, shifts=dist.global_shifts.grad,
+                 params=torch.cat([p.grad.reshape(-1) for p in net.parameters()]))
+    e = {}
+    for k in ("loss", "loss_rgb", "loss_depth", "l2_mean", "loss_pc", "loss_rgb_s"):
+        ref = float(ld_ref[k]); got = float(ld[k])
+        e["loss_" + k] = abs(got - ref) / max(abs(ref), 1e-6) if ref != 0 else abs(got)
+    for k in gref:
+        e["g_" + k] = rel(gours[k], gref[k]); e["env_" + k] = env[k]
+    e["cos_params"] = 1.0 - cosine(gours["params"], gref["params"])
+    _report("%s/%s" % (name, eng), **e)
+    for k in ("loss", "loss_rgb", "loss_depth", "l2_mean", "loss_pc", "loss_rgb_s"):
+        assert e["loss_" + k] < 1e-5, (k, e)
+    for k in ("r", "t", "scales", "shifts"):
+        assert e["g_" + k] < max(1e-4, 3 * e["env_" + k]), (k, e)
+    assert e["g_params"] < max(5e-4, 3 * e["env_params"]), e
+    assert e["cos_params"] < 1e-6, e
+
+
+@pytest.mark.parametrize("name", ["C2_render", "C3_ndc"])
+def test_render_outputs_vs_live_reference(name):
+    """nope_nerf.forward at full size: rgb, depth_pred, depth_gt <= 1e-4 of the live reference (same ray_idx, no jitter so that the two
+    sides need no RNG coupling; eval_mode False keeps the training-path arithmetic)."""
+    from nope_nerf_b200 import ops
+    ops.set_default_engine("tc")
+    c = CASES[name]; cfg = _cfg(c); V = c["V"]; idx = 3
+    torch.manual_seed(4321)
+    rig = RH.RefRig(cfg, V, "cuda")
+    state = _init_state(rig, V, 98)
+    data = _data(c, idx, 6)
+    H, W, N = c["H"], c["W"], c["N"]
+    ray_idx = torch.randperm(H * W, generator=torch.Generator().manual_seed(3))[:N].cuda()
+    trainer, net, pose, dist, model = _ours(cfg, V, state)
+    import model.common as mc                                          # the REFERENCE's helpers (oracle/_ref on sys.path)
+    p_full = mc.arange_pixels((H, W), 1)[1].cuda()
+    pix = p_full[:, ray_idx]
+    cam = data["img.camera_mat"].cuda(); smat = data["img.scale_mat"].cuda()
+    dpt = data["img.dpt"].cuda().unsqueeze(1)
+    outs = []
+    for (mod, ps, ds) in ((rig.model, rig.pose, rig.dist), (model, pose, dist)):
+        with torch.no_grad():
+            c2w = ps(idx); sc, sh = ds(idx)
+            out = mod(pix, ray_idx, cam, torch.inverse(c2w).unsqueeze(0), smat, "nope_nerf", it=0, eval_mode=False, depth_img=dpt * sc + sh,
+                      add_noise=False, img_size=(H, W))
+        outs.append(out)
+    e = dict(rgb=rel(outs[1]["rgb"], outs[0]["rgb"]), depth_pred=rel(outs[1]["depth_pred"], outs[0]["depth_pred"]),
+             depth_gt=rel(outs[1]["depth_gt"], outs[0]["depth_gt"]))
+    _report("render/%s" % name, **e)
+    assert max(e.values()) < 1e-4, e

@@ -21,7 +21,8 @@ from oracle import nerf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-RENDER_CASES = ["render_tanks_noise", "render_tanks_r0", "render_eval_ones", "render_ndc_distalpha", "render_oddflags"]
+RENDER_CASES = ["render_tanks_noise", "render_tanks_r0", "render_eval_ones", "render_ndc_distalpha", "render_oddflags",
+                "render_tanks_noise_damped", "render_ndc_distalpha_damped", "render_oddflags_damped", "render_eval_ones_damped"]
 REPORT = {}
 
 
@@ -50,7 +51,7 @@ def cuda(x, dtype=None):
 def run_case_cuda(g, engine):
     from nope_nerf_b200 import ops, _lib as L
     cfg = cfg_from_golden(g)
-    P = O.init_params(seed=int(g["seed"]), white_bkgd=cfg["white_background"])
+    P = O.init_params(seed=int(g["seed"]), white_bkgd=cfg["white_background"], hf_damp=bool(g.get("hf_damp", False)))
     flat = cuda(O.flatten_params(P))
     cam_id = int(g["cam_id"]); N, S, H, W = int(g["N"]), int(g["S"]), int(g["H"]), int(g["W"])
     r, t = cuda(g["r"]), cuda(g["t"])
@@ -87,41 +88,55 @@ def oracle64(g):
     return T.run_render(g, np.float64)
 
 
+def oracle32(g):
+    import test_oracle_golden as T
+    return T.run_render(g, np.float32)
+
+
 @pytest.mark.parametrize("name", RENDER_CASES)
 @pytest.mark.parametrize("eng", ["simt", "tc"])
 def test_render_vs_reference_golden(name, eng):
-    from nope_nerf_b200 import _lib as L
+    """Outputs: <= 1e-4 of the reference.  Gradients, two kinds of case:
+      * `*_damped` (oracle.init_params(hf_damp=True): no ReLU-gate switches between fp32 evaluation orders): every gradient
+        <= 1e-4 of the fp64 truth (MLP parameter digests 5e-4) and <= max(1e-4, 3 x the reference's own distance from it);
+      * default-initialised cases: gradients carry gate-switch noise (tests/test_oracle_golden.py::test_render_gate_matched_and_kxy):
+        <= max(1e-4, 3 x envelope), envelope = max(|reference - fp64|, |numpy fp32 - fp64|) = the spread of independent fp32
+        evaluations of the same step around the truth."""
     engine = dict(engines()).get(eng)
     if engine is None:
         pytest.skip("engine disabled")
     g = load_golden(name)
-    cfg = cfg_from_golden(g)
+    damped = bool(g.get("hf_damp", False))
     out, grads = run_case_cuda(g, engine)
     cam = int(g["cam_id"])
     o64, gr64, g_r64, g_t64, raw, _ = oracle64(g)
+    o32, gr32, g_r32, g_t32, _, _ = oracle32(g)
+    ss_ref = np.array([g["grad_scale"], g["grad_shift"]])
+    ss = lambda gr: np.array([(gr["depth"] * raw).sum(), gr["depth"].sum()])
+    # term -> (ours, reference, fp64 oracle, fp32 oracle)
+    terms = dict(c2w=(grads["c2w"], g["grad_c2w"], gr64["c2w"], gr32["c2w"]), r=(grads["r"], g["grad_r"][cam], g_r64, g_r32),
+                 t=(grads["t"], g["grad_t"][cam], g_t64, g_t32), ss=(grads["ss"], ss_ref, ss(gr64), ss(gr32)),
+                 kxy=(grads["kxy"], g["grad_kxy"], gr64["kxy"], gr32["kxy"]))
     e = dict(rgb=relmax(out["rgb"], g["rgb"]), depth_pred=relmax(out["depth_pred"], g["depth_pred"]),
              depth_gt=relmax(out["depth_gt"], g["depth_gt"]), alpha=relmax(out["alpha"], g["alpha"]),
              z=relmax(out["z_vals"], g["z_vals"]), c2w=relmax(out["c2w"], g["c2w"]),
-             g_c2w=relmax(grads["c2w"], g["grad_c2w"]), g_r=relmax(grads["r"], g["grad_r"][cam]),
-             g_t=relmax(grads["t"], g["grad_t"][cam]),
-             g_ss=relmax(grads["ss"], np.array([g["grad_scale"], g["grad_shift"]])),
-             g_params=check_param_digest(g, grads["params"]),
-             g_kxy_vs_oracle=relmax(grads["kxy"], gr64["kxy"]),
-             env_c2w=relmax(gr64["c2w"], g["grad_c2w"]), env_r=relmax(g_r64, g["grad_r"][cam]),
-             env_t=relmax(g_t64, g["grad_t"][cam]), env_params=check_param_digest(g, gr64["params"]),
-             env_ss=relmax(np.array([(gr64["depth"] * raw).sum(), gr64["depth"].sum()]), np.array([g["grad_scale"], g["grad_shift"]])))
+             g_params=check_param_digest(g, grads["params"]), env_params=max(check_param_digest(g, gr64["params"]),
+                                                                             check_param_digest(g, gr32["params"])))
+    for k, (ours, ref, t64, t32) in terms.items():
+        e["g_" + k] = relmax(ours, ref); e["g_%s_vs64" % k] = relmax(ours, t64); e["g_%s_vs32" % k] = relmax(ours, t32)
+        e["env_" + k] = max(relmax(t64, ref), relmax(t32, t64)); e["ref64_" + k] = relmax(t64, ref)
     _report("%s/%s" % (name, eng), **e)
     tol = 1e-4
     for k in ("rgb", "depth_pred", "depth_gt", "z", "c2w"):
         assert e[k] < tol, (k, e[k])
     assert e["alpha"] < 2e-4, e["alpha"]
-    floor = 2e-2 if cfg["occ_activation"] == "relu" else 1e-4
-    assert e["g_c2w"] < max(floor, 3 * e["env_c2w"]), e
-    assert e["g_r"] < max(floor, 3 * e["env_r"]), e
-    assert e["g_t"] < max(floor, 3 * e["env_t"]), e
-    assert e["g_ss"] < max(floor, 3 * e["env_ss"]), e
-    assert e["g_params"] < max(5e-4, floor, 3 * e["env_params"]), e
-    assert e["g_kxy_vs_oracle"] < max(10 * floor, 3e-3), e
+    for k in terms:
+        if damped:
+            assert e["g_%s_vs64" % k] < 1e-4, (k, e)
+            assert e["g_" + k] < max(1e-4, 3 * e["ref64_" + k]), (k, e)
+        else:
+            assert e["g_" + k] < max(1e-4, 3 * e["env_" + k]), (k, e)
+    assert e["g_params"] < max(5e-4, 3 * e["env_params"]), e
 
 
 def test_pose_expmap_kernels():
@@ -166,14 +181,22 @@ def _build_trainer(g, engine_name, with_ref):
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     opt_p = torch.optim.Adam(pose.parameters(), lr=5e-4)
     opt_d = torch.optim.Adam(dist.parameters(), lr=5e-4)
+    focal = opt_f = None
+    if "focal0" in g:                                   # train.py:140-147
+        focal = mdl.LearnFocal(True, False, order=2, init_focal=[1.0, 1.0]).to(dev)
+        with torch.no_grad():
+            focal.fx.copy_(torch.tensor(float(g["focal0"][0]))); focal.fy.copy_(torch.tensor(float(g["focal0"][1])))
+        opt_f = torch.optim.Adam(focal.parameters(), lr=1e-3)
     # use_cuda_graph=False: the golden comparison injects the reference's pixel / jitter draws by patching torch.randperm /
     # torch.rand, which must run eagerly (the same kernel sequence is what the graph path captures)
     trainer = mdl.Trainer(model, opt, cfg["training"], device=dev, optimizer_pose=opt_p, pose_param_net=pose,
-                          optimizer_distortion=opt_d, distortion_net=dist, use_cuda_graph=False)
+                          optimizer_distortion=opt_d, distortion_net=dist, optimizer_focal=opt_f, focal_net=focal, use_cuda_graph=False)
+    trainer._test_focal = focal
     return trainer, net, pose, dist
 
 
-@pytest.mark.parametrize("name,with_ref", [("train_render_only", False), ("train_full_losses", True), ("train_full_lastview", True)])
+@pytest.mark.parametrize("name,with_ref", [("train_render_only", False), ("train_full_losses", True), ("train_full_lastview", True),
+                                           ("train_learn_focal", True)])
 @pytest.mark.parametrize("eng", ["simt", "tc"])
 def test_trainer_step_vs_reference_golden(name, with_ref, eng, monkeypatch):
     if dict(engines()).get(eng) is None:
@@ -203,16 +226,25 @@ def test_trainer_step_vs_reference_golden(name, with_ref, eng, monkeypatch):
         worst["g_shifts_%d" % it] = relmax(dist.global_shifts.grad.cpu().numpy(), g["grad_shifts_%d" % it])
         grads = {n: p.grad.cpu().numpy() for n, p in net.named_parameters()}
         worst["g_params_%d" % it] = check_param_digest(g, grads, prefix="pg_%d." % it)
+        if "focal0" in g:
+            fo = trainer._test_focal
+            worst["g_focal_%d" % it] = relmax(np.array([fo.fx.grad.item(), fo.fy.grad.item()]), g["grad_focal_%d" % it])
+            for k in ("focalx", "focaly"):
+                ref = float(g["loss_%d.%s" % (it, k)].reshape(-1)[0])
+                worst["loss_%d_%s" % (it, k)] = abs(float(ld[k]) - ref) / abs(ref)
     worst["r_end"] = relmax(pose.r.detach().cpu().numpy() - g["r0"], g["r_end"] - g["r0"])
     worst["t_end"] = relmax(pose.t.detach().cpu().numpy() - g["t0"], g["t_end"] - g["t0"])
     worst["params_end"] = check_param_digest(g, {n: p.detach().cpu().numpy() for n, p in net.named_parameters()}, prefix="pend.")
+    if "focal0" in g:
+        fo = trainer._test_focal
+        worst["focal_end"] = relmax(np.array([fo.fx.item(), fo.fy.item()]) - g["focal0"], g["focal_end"] - g["focal0"])
     _report("%s/%s" % (name, eng), **worst)
     for k, v in worst.items():
         if k.startswith("loss"):
             assert v < 2e-4, (k, v)        # loss scalars (L1 sums of N*3 terms, fp32)
         elif k.startswith("g_"):
             assert v < 2e-3, (k, v)        # first-step gradients incl. the chamfer / warp terms (see module docstring)
-        elif k in ("r_end", "t_end"):
+        elif k in ("r_end", "t_end", "focal_end"):
             assert v < 5e-2, (k, v)        # Adam's first steps are ~ lr * sign(g): tiny gradients flip easily
         else:
             assert v < 1e-3, (k, v)
@@ -375,6 +407,97 @@ def test_cuda_graph_step_matches_eager_sequence():
     assert np.abs(lg - le).max() < 0.15 * np.abs(le).max(), (le, lg)   # later draws may differ (graph-safe philox offsets)
 
 
+@pytest.mark.parametrize("full", [False, True])
+def test_graph_replay_equals_eager_on_injected_draws(full, monkeypatch):
+    """The captured whole-step graph (render-only, and the FULL loss set with the reference-image stage on its forked stream) against
+    the same kernel sequence launched eagerly, on IDENTICAL pixel / jitter draws: torch.randperm / torch.rand are patched to hand out
+    persistent device buffers that the test refills before every step, so the replayed graph reads the new draws.  Loss weights
+    change during the run (annealing: epoch moves past scheduling_start) without re-capturing.  After 8 steps every parameter must
+    agree to the noise of fp32 atomics."""
+    import nope_nerf_b200.model as mdl
+    from nope_nerf_b200 import ops
+    from _cfg import default_cfg
+    ops.set_default_engine("tc")
+    H, W, V, N, S, hd, wd = 96, 128, 6, 256, 64, 24, 32
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    up = lambda t, size: torch.nn.functional.interpolate(t, size, mode="bilinear", align_corners=False)
+    frames = [dict(img=up(torch.rand(1, 3, 12, 16, generator=g), (H, W)).cuda(), dpt=(up(torch.rand(1, 1, 6, 8, generator=g), (hd, wd))[0] * 3 + 2).cuda())
+              for _ in range(V)]
+    draws = [(torch.randperm(H * W, generator=g)[:N].cuda(), torch.rand(N, S, generator=g).cuda()) for _ in range(8)]
+    ray_buf = torch.zeros(N, dtype=torch.int64, device=dev); noise_buf = torch.zeros(1, N, S, device=dev)
+    monkeypatch.setattr(torch, "randperm", lambda n, device=None: ray_buf)
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: noise_buf)
+    cam = torch.tensor([[1.2, 0, 0, 0], [0, -1.6, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], dtype=torch.float32)[None]
+    res = {}
+    for mode in (False, True):
+        cfg = default_cfg()
+        if not full:
+            cfg["training"]["pc_weight"] = [0.0, 0.0]; cfg["training"]["rgb_s_weight"] = [0.0, 0.0]
+        cfg["training"]["n_training_points"] = N; cfg["rendering"]["num_points"] = S
+        cfg["training"]["annealing_epochs"] = 10
+        net = mdl.OfficialStaticNerf(cfg)
+        net.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in O.init_params(seed=9, hf_damp=True).items()})
+        model = mdl.get_model(mdl.Renderer(net, cfg["rendering"], device=dev), cfg, device=dev)
+        pose = mdl.LearnPose(V, True, True, cfg).to(dev); dist = mdl.Learn_Distortion(V, True, True, cfg).to(dev)
+        with torch.no_grad():
+            pose.r.copy_(torch.randn(V, 3, generator=torch.Generator().manual_seed(5)) * 0.03); pose.t.copy_(torch.randn(V, 3, generator=torch.Generator().manual_seed(6)) * 0.03)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3); opt_p = torch.optim.Adam(pose.parameters(), lr=5e-4)
+        opt_d = torch.optim.Adam(dist.parameters(), lr=5e-4)
+        tr = mdl.Trainer(model, opt, cfg["training"], device=dev, optimizer_pose=opt_p, pose_param_net=pose, optimizer_distortion=opt_d,
+                         distortion_net=dist, use_cuda_graph=mode, pixel_sampler="randperm")
+        losses = []
+        for it in range(8):
+            ray_buf.copy_(draws[it][0]); noise_buf[0].copy_(draws[it][1])
+            i = (it * 2 + 1) % (V - 1)          # view pairs (i, i+1); the last view's role swap is covered by the golden tests
+            data = {"img": frames[i]["img"], "img.idx": torch.tensor([i]), "img.dpt": frames[i]["dpt"], "img.camera_mat": cam,
+                    "img.scale_mat": torch.eye(4)[None], "img.ref_imgs": frames[i + 1]["img"], "img.ref_dpts": frames[i + 1]["dpt"],
+                    "img.ref_idxs": torch.tensor([i + 1])}
+            ld = tr.train_step(data, it=it, epoch=it, scheduling_start=3, render_path=None)      # weights anneal from step 4 on
+            losses.append([ld[k].item() for k in ("loss", "loss_rgb", "loss_depth", "loss_pc", "loss_rgb_s")])
+        if mode:
+            gsteps = [v for v in tr._gsteps.values() if v]
+            assert len(gsteps) == 1 and gsteps[0].graph is not None and gsteps[0].calls == 8      # ONE capture served all weight values
+        res[mode] = (np.array(losses), net.flat_weights().detach().cpu().numpy().copy(), pose.r.detach().cpu().numpy().copy(),
+                     pose.t.detach().cpu().numpy().copy(), dist.global_shifts.detach().cpu().numpy().copy())
+    le, lg = res[False][0], res[True][0]
+    e = dict(loss=np.abs(le - lg).max() / np.abs(le).max(), w=relmax(res[True][1] - O.flatten_params(O.init_params(seed=9, hf_damp=True)),
+                                                                    res[False][1] - O.flatten_params(O.init_params(seed=9, hf_damp=True))),
+             r=relmax(res[True][2], res[False][2]), t=relmax(res[True][3], res[False][3]), shifts=relmax(res[True][4], res[False][4]))
+    _report("graph_vs_eager/%s" % ("full" if full else "render"), **e)
+    if full:
+        assert le[:, 3].min() > 0 and le[:, 4].min() > 0, le             # the reference-image terms were live
+    assert e["loss"] < 1e-5, (e, le, lg)
+    assert e["w"] < 2e-2 and e["r"] < 1e-3 and e["t"] < 1e-3 and e["shifts"] < 1e-3, e   # 8 Adam steps: tiny gradients flip sign of m/sqrt(v)
+
+
+def test_adam_resume_from_checkpoint_matches_torch():
+    """optimizer.state_dict() / load_state_dict() round trip (the reference's CheckpointIO, train.py:60-67, 249-271): after loading
+    a checkpoint taken at step 5 into a NEW Trainer, both the eager fused Adam and the graph path continue bias correction from the
+    loaded step, like torch.optim.Adam does."""
+    from nope_nerf_b200.model.training import _FlatAdam
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=gen).cuda()
+    grads = [torch.randn(1000, generator=gen).cuda() * 0.1 for _ in range(8)]
+    # torch reference: 8 uninterrupted steps
+    pr = torch.nn.Parameter(p0.clone()); opt_r = torch.optim.Adam([pr], lr=1e-2)
+    for g_ in grads:
+        pr.grad = g_.clone(); opt_r.step()
+    # ours: 5 steps, checkpoint, new optimizer + _FlatAdam, load, 3 more steps
+    pa = torch.nn.Parameter(p0.clone()); opt_a = torch.optim.Adam([pa], lr=1e-2); fa = _FlatAdam(opt_a)
+    for g_ in grads[:5]:
+        pa.grad = g_.clone(); fa.step()
+    sd = opt_a.state_dict()
+    assert int(sd["state"][0]["step"]) == 5
+    pb = torch.nn.Parameter(pa.detach().clone()); opt_b = torch.optim.Adam([pb], lr=1e-2); fb = _FlatAdam(opt_b)
+    opt_b.load_state_dict(sd)
+    for g_ in grads[5:]:
+        pb.grad = g_.clone(); fb.step()
+    assert fb.nsteps == 8 and int(opt_b.state_dict()["state"][0]["step"]) == 8
+    assert relmax(pb.detach().cpu().numpy(), pr.detach().cpu().numpy()) < 1e-6
+
+
 def test_full_frame_renderer_vs_reference_golden():
     """Extract_Images.render_frame (config 4 caller, model/extracting_images.py:52-77): the whole 27x48 frame in one call;
     the golden's 32 rays (eval mode, ones prior, init_c2w pose) must come out identical."""
@@ -492,10 +615,7 @@ def test_pixel_sampler_distinct_and_uniform():
 @pytest.mark.parametrize("name", ["train_full_losses", "train_full_lastview"])
 def test_native_ref_stage_vs_oracle(name):
     """nnb_refstage (fused kernels of the reference-image stage) vs oracle.ref_stage on the full-loss goldens' inputs.
-    EXPERIMENTAL: the kernels were written at the end of round 1 without GPU time left (their per-point arithmetic is checked
-    on the CPU, tests/test_host.py); this test runs only with NNB_EXPERIMENTAL=1 until it has passed on hardware once."""
-    if os.environ.get("NNB_EXPERIMENTAL", "0") != "1":
-        pytest.skip("set NNB_EXPERIMENTAL=1 (kernels not yet validated on hardware)")
+    (First green on hardware in round 2: losses 1e-7, gradients 1e-6.)"""
     from nope_nerf_b200 import ops
     from test_host import _ref_stage_case
     c = _ref_stage_case(name)
@@ -504,29 +624,29 @@ def test_native_ref_stage_vs_oracle(name):
                         c["c2w"].astype(np.float64), c["c2wr"].astype(np.float64), c["dist"][0], c["dist"][1], c["distr"][0], c["distr"][1],
                         c["is_last"], c["kx"], c["ky"], cfg=c["cfg"])
     c2w = cuda(c["c2w"]).requires_grad_(True); dist = torch.tensor(c["dist"], device="cuda", requires_grad=True)
+    kx = torch.tensor(c["kx"], device="cuda", requires_grad=True); ky = torch.tensor(c["ky"], device="cuda", requires_grad=True)
     total, losses = ops.refstage(c2w, dist, cuda(c["c2wr"]), torch.tensor(c["distr"], device="cuda"), cuda(g["img"]), cuda(g["ref"]), cuda(g["dpt"]),
-                                 cuda(g["rdpt"]), c["is_last"], c["kx"], c["ky"])
+                                 cuda(g["rdpt"]), c["is_last"], kx, ky)
     total.backward()
     e = dict(loss_pc=abs(losses[0].item() - l["loss_pc"]) / l["loss_pc"], loss_rgb_s=abs(losses[1].item() - l["loss_rgb_s"]) / l["loss_rgb_s"],
              g_c2w=relmax(c2w.grad.cpu().numpy()[:3], gr["c2w"][:3]),
-             g_dist=relmax(dist.grad.cpu().numpy(), np.array([gr["scale"], gr["shift"]])))
+             g_dist=relmax(dist.grad.cpu().numpy(), np.array([gr["scale"], gr["shift"]])),
+             g_kxy=relmax(np.array([kx.grad.item(), ky.grad.item()]), gr["kxy"]))
     _report("native_ref_stage/%s" % name, **e)
-    assert e["loss_pc"] < 1e-5 and e["loss_rgb_s"] < 1e-5 and e["g_c2w"] < 1e-4 and e["g_dist"] < 1e-4, e
+    assert e["loss_pc"] < 1e-5 and e["loss_rgb_s"] < 1e-5 and e["g_c2w"] < 1e-4 and e["g_dist"] < 1e-4 and e["g_kxy"] < 1e-4, e
 
 
-@pytest.mark.parametrize("N,S", [(5, 32), (3, 64), (7, 32), (130, 32)])
+@pytest.mark.parametrize("N,S", [(5, 32), (3, 64), (7, 32), (130, 32), (33, 64), (999, 128), (9, 256)])
 def test_ragged_last_tile_tc_vs_simt(N, S):
     """N*S not a multiple of the 128-sample tile: the tcgen05 engine pads the last tile with clamped rows whose cotangents are
-    zero; outputs and gradients must agree with the exact-fp32 engine.  Every size the suite ran on hardware so far is a
-    multiple of 128 samples, so this case runs with NNB_EXPERIMENTAL=1 until it has passed once."""
-    if os.environ.get("NNB_EXPERIMENTAL", "0") != "1":
-        pytest.skip("set NNB_EXPERIMENTAL=1 (size class not yet run on hardware)")
+    zero; outputs and gradients must agree with the exact-fp32 engine (weights from init_params(hf_damp=True), so that the
+    comparison of the two engines' GRADIENTS is not dominated by single ReLU-gate switches on a handful of rays)."""
     from nope_nerf_b200 import ops, _lib as L
     if len(engines()) < 2:
         pytest.skip("needs both engines")
     H, W = 40, 56
     gen = torch.Generator(device="cuda").manual_seed(N * 1000 + S)
-    flat = cuda(O.flatten_params(O.init_params(seed=5)))
+    flat = cuda(O.flatten_params(O.init_params(seed=5, hf_damp=True)))
     r = torch.randn(3, 3, device="cuda", generator=gen) * 0.05; t = torch.randn(3, 3, device="cuda", generator=gen) * 0.05
     c2w = torch.empty(4, 4, device="cuda"); ops.pose_fwd_raw(r, t, None, 1, c2w)
     cam = torch.diag(torch.tensor([1.2, -1.6, -1.0, 1.0])).cuda()
@@ -548,4 +668,4 @@ def test_ragged_last_tile_tc_vs_simt(N, S):
     rel = lambda x, y: ((x - y).abs().max() / x.abs().max().clamp_min(1e-30)).item()
     e = dict(rgb=rel(a[0], b[0]), dp=rel(a[1], b[1]), gw=rel(a[2], b[2]), gc=rel(a[3], b[3]), gss=rel(a[4], b[4]))
     _report("ragged/%dx%d" % (N, S), **e)
-    assert e["rgb"] < 1e-4 and e["dp"] < 1e-4 and e["gw"] < 2e-3 and e["gc"] < 2e-3 and e["gss"] < 2e-3, e
+    assert e["rgb"] < 1e-4 and e["dp"] < 1e-4 and e["gw"] < 5e-4 and e["gc"] < 1e-4 and e["gss"] < 1e-4, e

@@ -199,8 +199,8 @@ def _ref_stage_case(name, detach=False, scale_pcs=True):
 
 
 @pytest.mark.parametrize("name", ["train_full_losses", "train_full_lastview"])
-@pytest.mark.parametrize("detach,scale_pcs", [(False, True), (True, True), (False, False)])
-def test_refstage_device_math_on_host(name, detach, scale_pcs, tmp_path):
+@pytest.mark.parametrize("detach,scale_pcs,shift_first", [(False, True, False), (True, True, False), (False, False, False), (False, True, True)])
+def test_refstage_device_math_on_host(name, detach, scale_pcs, shift_first, tmp_path):
     """nope_nerf_b200/csrc/nnb_refstage.cuh holds the per-point arithmetic of the reference-image stage as __host__ __device__
     functions; tools/refstage_host_check.cu runs exactly those functions on the CPU (plus a brute-force chamfer with the
     kernels' arithmetic).  Compared here with oracle.ref_stage, which is pinned to the reference's full-loss train steps."""
@@ -214,6 +214,7 @@ def test_refstage_device_math_on_host(name, detach, scale_pcs, tmp_path):
         os.makedirs(os.path.dirname(exe), exist_ok=True)
         subprocess.check_call([nvcc, "-O1", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src])
     c = _ref_stage_case(name, detach, scale_pcs)
+    c["cfg"]["shift_first"] = shift_first
     g = c["g"]
     H, W = g["img"].shape[1:]; hd, wd = g["dpt"].shape
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
@@ -222,7 +223,7 @@ def test_refstage_device_math_on_host(name, detach, scale_pcs, tmp_path):
         np.array([c["kx"], c["ky"], 0.01, c["dist"][0], c["dist"][1], c["distr"][0], c["distr"][1], 1.0, 1.0], np.float32).tofile(fo)
         for arr in (c["c2w"], c["c2wr"], g["img"], g["ref"], g["dpt"], g["rdpt"]):
             np.ascontiguousarray(arr, np.float32).tofile(fo)
-    subprocess.check_call([exe, fin, fout])
+    subprocess.check_call([exe, fin, fout, "1" if shift_first else "0"])
     o = np.fromfile(fout, np.float32)
     l, gr = O.ref_stage(g["img"], g["ref"], g["dpt"], g["rdpt"], c["c2w"], c["c2wr"], c["dist"][0], c["dist"][1], c["distr"][0], c["distr"][1],
                         c["is_last"], np.float32(c["kx"]), np.float32(c["ky"]), cfg=c["cfg"])
@@ -230,3 +231,4 @@ def test_refstage_device_math_on_host(name, detach, scale_pcs, tmp_path):
     from _util import relmax
     assert relmax(o[2:18].reshape(4, 4)[:3], gr["c2w"][:3]) < 2e-5
     assert abs(o[18] - gr["scale"]) < 2e-5 * max(abs(gr["scale"]), 1.0) and abs(o[19] - gr["shift"]) < 2e-5 * max(abs(gr["shift"]), 1.0)
+    assert relmax(o[20:22], gr["kxy"]) < 5e-5, (o[20:22], gr["kxy"])          # d/d(kx, ky): what LearnFocal receives from this stage

@@ -70,7 +70,7 @@ def build_model(mdl, cfg, P):
     return net, rend, model
 
 
-def case_render(mdl, name, overrides, N, S, H, W, hd, wd, eval_mode, add_noise, seed, pose_mode, prior="dpt"):
+def case_render(mdl, name, overrides, N, S, H, W, hd, wd, eval_mode, add_noise, seed, pose_mode, prior="dpt", hf_damp=False):
     """nope_nerf.forward (model/network.py:19-33 -> model/rendering.py:36-167) + autograd grads."""
     import torch
     from oracle import nerf_oracle as O
@@ -79,7 +79,7 @@ def case_render(mdl, name, overrides, N, S, H, W, hd, wd, eval_mode, add_noise, 
         sec, key = k.split(".")
         cfg[sec][key] = v
     cfg["rendering"]["num_points"] = S
-    P = O.init_params(seed=seed, white_bkgd=cfg["rendering"]["white_background"])
+    P = O.init_params(seed=seed, white_bkgd=cfg["rendering"]["white_background"], hf_damp=hf_damp)
     net, rend, model = build_model(mdl, cfg, P)
     rng = np.random.default_rng(seed + 1)
     V = 5
@@ -98,7 +98,9 @@ def case_render(mdl, name, overrides, N, S, H, W, hd, wd, eval_mode, add_noise, 
     cam_id = 2
     fx = 0.6 * W
     kx, ky = 2 * fx / W, -2 * fx / H
-    camera_mat = torch.tensor([[[kx, 0, 0, 0], [0, ky, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]]], dtype=torch.float32)
+    kxy = torch.tensor([kx, ky], dtype=torch.float32, requires_grad=True)        # d/dK as LearnFocal needs it (training.py:247-252)
+    z4 = torch.zeros(4); one = torch.ones(1)
+    camera_mat = torch.cat([kxy[0:1], z4, kxy[1:2], z4, -one, z4, one]).view(1, 4, 4)
     scale_mat = torch.eye(4).unsqueeze(0)
     if prior == "dpt":
         dpt = rng.uniform(0.6, 7.2, (hd, wd)).astype(np.float32)
@@ -129,7 +131,7 @@ def case_render(mdl, name, overrides, N, S, H, W, hd, wd, eval_mode, add_noise, 
     scalar = (out["rgb"] * torch.from_numpy(g_rgb)).sum() + (out["depth_pred"] * torch.from_numpy(g_dp)).sum() \
         + (out["depth_gt"] * torch.from_numpy(g_dg)).sum()
     scalar.backward()
-    rec = dict(N=N, S=S, H=H, W=W, seed=seed, cam_id=cam_id, kx=kx, ky=ky, eval_mode=eval_mode,
+    rec = dict(N=N, S=S, H=H, W=W, seed=seed, cam_id=cam_id, kx=kx, ky=ky, eval_mode=eval_mode, hf_damp=hf_damp,
                add_noise=add_noise, r=r, t=t, dpt=dpt, ray_idx=ray_idx, scale=1.07, shift=-0.03,
                pixels=p[0].detach().numpy(), c2w=c2w.detach().numpy(),
                g_rgb=g_rgb[0], g_dp=g_dp, g_dg=g_dg,
@@ -137,7 +139,7 @@ def case_render(mdl, name, overrides, N, S, H, W, hd, wd, eval_mode, add_noise, 
                depth_gt=out["depth_gt"].detach().numpy(), z_vals=out["z_vals"].detach().numpy(),
                alpha=out["alpha"].detach().numpy(),
                grad_c2w=c2w.grad.numpy(), grad_r=pose.r.grad.numpy(), grad_t=pose.t.grad.numpy(),
-               grad_scale=scale.grad.numpy(), grad_shift=shift.grad.numpy())
+               grad_scale=scale.grad.numpy(), grad_shift=shift.grad.numpy(), grad_kxy=kxy.grad.numpy())
     if init is not None:
         rec["init_c2w"] = init
     if noise is not None:
@@ -204,7 +206,7 @@ def case_pose(mdl, name):
     print("wrote", name)
 
 
-def case_train_step(mdl, name, with_ref, steps, N, S, H, W, hd, wd, seed, last_view=False):
+def case_train_step(mdl, name, with_ref, steps, N, S, H, W, hd, wd, seed, last_view=False, learn_focal=False):
     """Trainer.train_step (model/training.py:67-97) for `steps` iterations on one synthetic pair."""
     import torch
     from oracle import nerf_oracle as O
@@ -228,10 +230,15 @@ def case_train_step(mdl, name, with_ref, steps, N, S, H, W, hd, wd, seed, last_v
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     opt_p = torch.optim.Adam(pose.parameters(), lr=5e-4)
     opt_d = torch.optim.Adam(dist.parameters(), lr=5e-4)
-    trainer = mdl.Trainer(model, opt, cfg["training"], device=torch.device("cpu"), optimizer_pose=opt_p,
-                          pose_param_net=pose, optimizer_distortion=opt_d, distortion_net=dist)
     fx = 0.6 * W
     kx, ky = 2 * fx / W, -2 * fx / H
+    focal = opt_f = None
+    if learn_focal:                                      # train.py:140-147: init_focal = [K00, -K11], order 2, Adam(focal_lr)
+        focal = mdl.LearnFocal(True, False, order=2, init_focal=[kx * 1.03, -ky * 0.98])
+        opt_f = torch.optim.Adam(focal.parameters(), lr=cfg["training"]["focal_lr"])
+    trainer = mdl.Trainer(model, opt, cfg["training"], device=torch.device("cpu"), optimizer_pose=opt_p,
+                          pose_param_net=pose, optimizer_distortion=opt_d, distortion_net=dist, optimizer_focal=opt_f,
+                          focal_net=focal)
     cam = np.array([[kx, 0, 0, 0], [0, ky, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], np.float32)
     idx = V - 1 if last_view else 1
     ref_idx = idx - 1 if last_view else idx + 1
@@ -244,6 +251,8 @@ def case_train_step(mdl, name, with_ref, steps, N, S, H, W, hd, wd, seed, last_v
             "img.ref_idxs": torch.tensor([ref_idx])}
     rec = dict(N=N, S=S, H=H, W=W, V=V, seed=seed, idx=idx, ref_idx=ref_idx, kx=kx, ky=ky, img=img[0], ref=ref[0],
                dpt=dpt[0], rdpt=rdpt[0], r0=r0, t0=t0, scales0=sc0, shifts0=sh0, steps=steps, with_ref=with_ref)
+    if learn_focal:
+        rec["focal0"] = np.array([focal.fx.item(), focal.fy.item()], np.float32)
     for it in range(steps):
         torch.manual_seed(500 + it)
         ray_idx = torch.randperm(H * W)[:N].numpy().copy()
@@ -257,11 +266,15 @@ def case_train_step(mdl, name, with_ref, steps, N, S, H, W, hd, wd, seed, last_v
         gz = lambda prm: np.zeros(tuple(prm.shape), np.float32) if prm.grad is None else prm.grad.numpy().copy()
         rec["grad_scales_%d" % it] = gz(dist.global_scales)   # None when the view's scale is the fixed constant
         rec["grad_shifts_%d" % it] = gz(dist.global_shifts)
+        if learn_focal:
+            rec["grad_focal_%d" % it] = np.array([focal.fx.grad.item(), focal.fy.grad.item()], np.float32)
         for n, prm in net.named_parameters():
             for kk, vv in digest(n, prm.grad.numpy()).items():
                 rec["pg_%d.%s.%s" % (it, n, kk)] = vv
     rec["r_end"] = pose.r.detach().numpy(); rec["t_end"] = pose.t.detach().numpy()
     rec["scales_end"] = dist.global_scales.detach().numpy(); rec["shifts_end"] = dist.global_shifts.detach().numpy()
+    if learn_focal:
+        rec["focal_end"] = np.array([focal.fx.item(), focal.fy.item()], np.float32)
     for n, prm in net.named_parameters():
         for kk, vv in digest(n, prm.detach().numpy()).items():
             rec["pend.%s.%s" % (n, kk)] = vv
@@ -309,6 +322,18 @@ def main():
         case_render(mdl, "render_oddflags", {"rendering.white_background": True, "rendering.use_ray_dir": False,
                                              "rendering.normalise_ray": False, "model.occ_activation": "relu"},
                     N=32, S=32, H=30, W=40, hd=12, wd=21, eval_mode=False, add_noise=False, seed=25, pose_mode="rand")
+    if "render" in which or "damped" in which:
+        # well-conditioned twins (oracle.init_params(hf_damp=True)): gradients gated at 1e-4 without an envelope term
+        case_render(mdl, "render_tanks_noise_damped", {}, N=24, S=128, H=30, W=40, hd=12, wd=21, eval_mode=False,
+                    add_noise=True, seed=21, pose_mode="rand", hf_damp=True)
+        case_render(mdl, "render_ndc_distalpha_damped", {"rendering.sample_option": "ndc", "rendering.dist_alpha": True,
+                                                         "rendering.depth_range": [0.0, 1.0]},
+                    N=24, S=128, H=30, W=40, hd=16, wd=20, eval_mode=False, add_noise=True, seed=24, pose_mode="rand", hf_damp=True)
+        case_render(mdl, "render_oddflags_damped", {"rendering.white_background": True, "rendering.use_ray_dir": False,
+                                                    "rendering.normalise_ray": False, "model.occ_activation": "relu"},
+                    N=32, S=32, H=30, W=40, hd=12, wd=21, eval_mode=False, add_noise=False, seed=25, pose_mode="rand", hf_damp=True)
+        case_render(mdl, "render_eval_ones_damped", {}, N=32, S=64, H=27, W=48, hd=27, wd=48, eval_mode=True,
+                    add_noise=False, seed=23, pose_mode="init", prior="ones", hf_damp=True)
     if "chamfer" in which:
         case_chamfer(mdl, "chamfer_dense", 193, 160, 41)
     if "train" in which:
@@ -316,6 +341,8 @@ def main():
         case_train_step(mdl, "train_full_losses", True, steps=2, N=48, S=32, H=24, W=32, hd=16, wd=24, seed=32)
         case_train_step(mdl, "train_full_lastview", True, steps=1, N=48, S=32, H=24, W=32, hd=16, wd=24, seed=33,
                         last_view=True)
+    if "focal" in which or "train" in which:
+        case_train_step(mdl, "train_learn_focal", True, steps=2, N=48, S=32, H=24, W=32, hd=16, wd=24, seed=34, learn_focal=True)
 
 
 if __name__ == "__main__":

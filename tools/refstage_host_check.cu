@@ -3,7 +3,8 @@
 //   refstage_host_check <in.bin> <out.bin>
 // in : int32[8] {H,W,hd,wd,ratio,is_last,scale_pcs,detach_rgbs_scale}, float32[9] {kx,ky,nl,s_cur,h_cur,s_ref,h_ref,w_pc,w_rgb_s},
 //      c2w_cur[16], c2w_ref[16], img_cur[3HW], img_ref[3HW], dpt_cur[hd*wd], dpt_ref[hd*wd]
-// out: float32 {loss_pc, loss_rgb_s, g_c2w[16], g_scale, g_shift}
+// out: float32 {loss_pc, loss_rgb_s, g_c2w[16], g_scale, g_shift, g_kx, g_ky}
+// optional 4th argument '1': shift_first
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -20,6 +21,7 @@ int main(int argc, char** argv) {
   G.is_last = hi[5]; G.scale_pcs = hi[6]; G.detach_rgbs_scale = hi[7];
   G.kx = hf[0]; G.ky = hf[1]; G.nl = hf[2]; G.s_cur = hf[3]; G.h_cur = hf[4]; G.s_ref = hf[5]; G.h_ref = hf[6];
   const float w_pc = hf[7], w_rgb_s = hf[8];
+  G.shift_first = (argc > 3 && argv[3][0] == '1') ? 1 : 0; G.w_pc = w_pc; G.w_rgb_s = w_rgb_s;
   std::vector<float> img_cur(3 * (size_t)G.H * G.W), img_ref(img_cur.size()), dpt_cur((size_t)G.hd * G.wd), dpt_ref(dpt_cur.size());
   if (fread(img_cur.data(), 4, img_cur.size(), f) != img_cur.size() || fread(img_ref.data(), 4, img_ref.size(), f) != img_ref.size() ||
       fread(dpt_cur.data(), 4, dpt_cur.size(), f) != dpt_cur.size() || fread(dpt_ref.data(), 4, dpt_ref.size(), f) != dpt_ref.size()) return 5;
@@ -66,13 +68,14 @@ int main(int argc, char** argv) {
     }
   }
   const float inv_nv = (w_rgb_s != 0.f && nvalid > 0) ? w_rgb_s / (3.f * (float)nvalid) : 0.f;
-  float acc[15] = {0};
+  float acc[refstage::kAcc] = {0};
   for (int i = 0; i < P; ++i) refstage::point_backward(G, img1, img2, pts[i], &gXs[3 * i], &gYs[3 * i], inv_nv, acc);
-  float out[20];
+  float out[22];
   out[0] = loss_pc; out[1] = nvalid > 0 ? sum_abs / (3.f * (float)nvalid) : 0.f;
   refstage::finish(G, c2w_cur, c2w_ref, acc, out + 2, out + 18, out + 19);
   f = fopen(argv[2], "wb");
   if (!f) return 6;
-  fwrite(out, 4, 20, f); fclose(f);
+  out[20] = acc[15]; out[21] = acc[16];
+  fwrite(out, 4, 22, f); fclose(f);
   return 0;
 }
