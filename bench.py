@@ -237,7 +237,8 @@ def run_ours(args):
         dist.barrier()
     # ---- headline: device-resident inputs, EXACTLY K timed steps after warm-up + settling ----
     cs = ClockSampler(local) if rank == 0 else None
-    ms, ld = timed(trainer, devd, K, Wm, sync_loss=False, settle_s=1.0)
+    ms_burst, _ = timed(trainer, devd, K, Wm, sync_loss=False)               # right after warm-up: boost clocks (round-1 methodology)
+    ms, ld = timed(trainer, devd, K, 0, sync_loss=False, settle_s=1.0)        # headline: after ~1 s of untimed steps (power-capped regime)
     ms_sus, _ = timed(trainer, devd, 1000, 0, sync_loss=False)
     clocks = cs.stop() if cs else {}
     launches = trainer.graph_kernel_nodes()
@@ -286,6 +287,8 @@ def run_ours(args):
                            "l2_policy": "no flush: each step streams a >1 GB activation stash, far larger than the 126 MB L2",
                            "settle": "W warm-up steps + ~1 s of untimed steps before the K timed steps"},
                 "sustained": {"steps": 1000, "ms_per_step": round(ms_sus / 1000, 4), "value": round(samples_per_step * 1000 / (ms_sus / 1e3), 1)},
+                "burst": {"steps": K, "ms_per_step": round(ms_burst / K, 4), "value": round(samples_per_step * K / (ms_burst / 1e3), 1),
+                          "note": "K steps timed right after the W warm-up steps, before clocks / power settle (how round 1 measured)"},
                 "e2e": {"value": round(e2e, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / K, 4),
                         "h2d_bytes_per_step": int(n_local * 3 * 32 + HD * WD * 4 + 64 + 16) * world, "d2h_bytes_per_step": 4 * world,
                         "sustained_ms_per_step": round(ms_e2e_sus / 300, 4),
@@ -386,11 +389,13 @@ def reference_on_device(device, steps, warm, budget_s):
         if device != "cpu": torch.cuda.synchronize()
         t0 = time.perf_counter()
         ld = rig.train_step(host[i % 2], it=i + 1)
-        float(ld["loss"])                                       # train.py:212 reads the loss every step
+        float(ld["loss"].detach())                              # train.py:212 reads the loss every step
         if device != "cpu": torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
-        if i >= warm + 2 and time.perf_counter() - t_start > budget_s:
-            break
+        if i == 0 and ts[0] > budget_s / 4:
+            warm = 1                                            # very slow host: one warm-up step has to do
+        if i >= warm and time.perf_counter() - t_start + ts[-1] > budget_s:
+            break                                               # bounded run: at least one timed step, then stop inside the budget
     ts = sorted(ts[warm:])
     med = ts[len(ts) // 2]
     return {"value": round(NRAYS * S / med, 1), "unit": "ray-samples/s", "sec_per_step": round(med, 4), "steps_timed": len(ts),
@@ -401,7 +406,9 @@ def reference_on_device(device, steps, warm, budget_s):
 
 def cpu_reference(steps, warm, budget_s):
     import torch
-    torch.set_num_threads(os.cpu_count())
+    # intra-op threads: all cores up to 32 -- on the 128-core GPU box the reference's step (thousands of small ATen ops) measured 59.6 s
+    # with 128 threads (r2 run 2); NNB_REF_THREADS overrides
+    torch.set_num_threads(int(os.environ.get("NNB_REF_THREADS", min(os.cpu_count() or 1, 32))))
     from oracle import ref_harness as RH
     if RH.available():
         r = reference_on_device("cpu", steps, warm, budget_s)
@@ -432,7 +439,7 @@ def run_reference(args):
     if rank != 0:
         return
     # torchrun pins OMP_NUM_THREADS=1 for its workers: the reference arm is ONE process that should use every host core
-    n = os.cpu_count() or 1
+    n = int(os.environ.get("NNB_REF_THREADS", min(os.cpu_count() or 1, 32)))
     os.environ["OMP_NUM_THREADS"] = str(n); os.environ["MKL_NUM_THREADS"] = str(n)
     K, Wm = args.steps, args.warmup
     cb = cpu_reference(steps=K, warm=max(1, min(Wm, 2)), budget_s=150.0)

@@ -81,6 +81,10 @@ typedef struct nnb_render_bwd_args {
   float* g_cam;     /* [16] ([0],[5] written) or NULL */
   float* g_depth;   /* [N] d/d prior depth (overwritten) or NULL */
   float* g_scale_shift; /* [2] d/d scale, d/d shift when depth_map is used, or NULL */
+  /* 0 = whole backward.  The tcgen05 backward can be issued in two calls so that the caller may fork independent work (the
+   * reference-image stage) beside the HBM-bound weight-gradient kernel: 1 = compositing adjoint + data-gradient chain,
+   * 2 = weight gradients + ray adjoint.  Other engines do everything in phase 1 (or 0) and nothing in phase 2. */
+  uint32_t phase;
 } nnb_render_bwd_args;
 
 const char* nnb_last_error(void);
@@ -172,6 +176,35 @@ typedef struct nnb_refstage_args {
 } nnb_refstage_args;
 size_t nnb_refstage_workspace_bytes(int32_t h_d, int32_t w_d, int32_t pc_ratio);
 int nnb_refstage(const nnb_refstage_args* args, void* stream);
+
+/* ---- data-parallel exchange over NVLink peer memory (new component) --------------------------------------
+ * The reference has no distributed code; the B200 design shards a step's rays (or views) over the GPUs of one box and needs ONE
+ * sum of the flat gradient buffer per step.  nnb_allreduce_adam does that sum with P2P loads from every rank's buffer and applies
+ * the three torch.optim.Adam updates (train.py:58,99,117) in the same kernel; it is captured in the step's CUDA graph.
+ * Buffers come from nnb_ipc_alloc (cudaMalloc + CUDA IPC handle); peers map them with nnb_ipc_open. */
+#define NNB_MAX_RANKS 8
+#define NNB_FLAG_PAD_BYTES 256      /* per-rank flag pad: uint32 [2][NNB_MAX_RANKS] + local counters; zero it once after allocation */
+int nnb_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle_out[64]);
+int nnb_ipc_open(const unsigned char handle[64], void** peer_ptr);
+int nnb_ipc_close(void* peer_ptr);
+int nnb_ipc_free(void* dev_ptr);
+typedef struct nnb_adam_seg {       /* one parameter tensor (or flat group) inside the gradient buffer */
+  float* p; float* m; float* v;     /* parameters and Adam moments (local) */
+  int64_t offset, count;            /* position of its gradient in the flat buffer */
+  const float* lr_dev; const int32_t* step_dev;   /* device-resident learning rate and 1-based step (as nnb_adam_step_dev) */
+  float beta1, beta2, eps;
+} nnb_adam_seg;
+typedef struct nnb_allreduce_adam_args {
+  const float* peer_grads[NNB_MAX_RANKS];   /* every rank's flat gradient buffer (own entry = local buffer), pre-scaled by 1/world */
+  uint32_t* peer_flags[NNB_MAX_RANKS];      /* every rank's flag pad (NNB_FLAG_PAD_BYTES) */
+  int32_t world, rank;
+  int64_t n_total;                  /* floats in the buffer (multiple of 4) */
+  float* reduced_out;               /* [n_total] local copy of the summed gradient (what .grad shows) or NULL */
+  nnb_adam_seg segs[8]; int32_t nsegs;
+} nnb_allreduce_adam_args;
+/* Sums the buffers of all ranks (rank order: bit-identical on every rank), applies Adam to every segment, writes the sum to
+ * reduced_out and ZEROES the local gradient buffer for the next step.  Every rank must call it the same number of times. */
+int nnb_allreduce_adam(const nnb_allreduce_adam_args* args, void* stream);
 
 /* torch.optim.Adam step (train.py:58,99,117 defaults) over one flat buffer. step_count is the
  * 1-based step; lr/betas/eps as torch. */

@@ -27,7 +27,7 @@ class RenderArgs(C.Structure):
 
 class RenderBwdArgs(C.Structure):
     _fields_ = [("fwd", RenderArgs), ("g_rgb", _f), ("g_depth_pred", _f), ("g_depth_gt", _f),
-                ("g_weights", _f), ("g_c2w", _f), ("g_cam", _f), ("g_depth", _f), ("g_scale_shift", _f)]
+                ("g_weights", _f), ("g_c2w", _f), ("g_cam", _f), ("g_depth", _f), ("g_scale_shift", _f), ("phase", C.c_uint32)]
 
 
 class RefStageArgs(C.Structure):
@@ -37,6 +37,20 @@ class RefStageArgs(C.Structure):
                 ("losses", _f), ("g_c2w", _f), ("g_dist", _f), ("workspace", _f), ("workspace_bytes", C.c_size_t),
                 ("img_pp", _f), ("cam", _f), ("cam_idx_dev", _f), ("num_cams", C.c_int32), ("weights_dev", _f),
                 ("g_kxy", _f), ("loss_total", _f), ("grad_scale", C.c_float)]
+
+
+MAX_RANKS = 8
+FLAG_PAD_BYTES = 256
+
+
+class AdamSeg(C.Structure):
+    _fields_ = [("p", _f), ("m", _f), ("v", _f), ("offset", C.c_int64), ("count", C.c_int64), ("lr_dev", _f), ("step_dev", _f),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
+class AllreduceAdamArgs(C.Structure):
+    _fields_ = [("peer_grads", _f * MAX_RANKS), ("peer_flags", _f * MAX_RANKS), ("world", C.c_int32), ("rank", C.c_int32),
+                ("n_total", C.c_int64), ("reduced_out", _f), ("segs", AdamSeg * 8), ("nsegs", C.c_int32)]
 
 
 def _load():
@@ -72,6 +86,11 @@ def _load():
     lib.nnb_refstage_workspace_bytes.restype = C.c_size_t
     lib.nnb_refstage_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.nnb_refstage.argtypes = [C.POINTER(RefStageArgs), C.c_void_p]
+    lib.nnb_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]
+    lib.nnb_ipc_open.argtypes = [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+    lib.nnb_ipc_close.argtypes = [C.c_void_p]
+    lib.nnb_ipc_free.argtypes = [C.c_void_p]
+    lib.nnb_allreduce_adam.argtypes = [C.POINTER(AllreduceAdamArgs), C.c_void_p]
     return lib
 
 

@@ -30,6 +30,7 @@ cudaError_t launch_chamfer_full(const float*, int, const float*, int, unsigned l
 cudaError_t launch_adam(float*, const float*, float*, float*, int64_t, int, float, float, float, float, cudaStream_t);
 size_t refstage_workspace_bytes(int hd, int wd, int ratio);
 cudaError_t launch_refstage(const nnb_refstage_args& a, cudaStream_t st);
+cudaError_t launch_allreduce_adam(const nnb_allreduce_adam_args& a, cudaStream_t st);
 
 // optional profiling hook (bench.py): CUDA events recorded between the kernels of one call
 static cudaEvent_t* g_prof_events = nullptr;
@@ -116,12 +117,13 @@ int nnb_render_bwd(const nnb_render_bwd_args* b, void* stream) {
   int rc = check_args(&b->fwd); if (rc) return rc;
   if (!(b->fwd.flags & NNB_STASH)) return fail(-6, "nnb_render_bwd needs the forward call to have run with NNB_STASH");
   if (!b->g_rgb || !b->g_c2w) return fail(-3, "g_rgb and g_c2w must be non-null");
+  if (b->phase > 2) return fail(-2, "nnb_render_bwd: phase must be 0, 1 or 2");
   WsLayout L = make_layout(b->fwd.N, b->fwd.S, b->fwd.flags, b->fwd.engine);
   cudaError_t e;
 #ifdef NNB_WITH_TC
   if (b->fwd.engine == NNB_ENGINE_TC) e = tc_render_bwd(*b, L, (cudaStream_t)stream); else
 #endif
-  e = simt_render_bwd(*b, L, (cudaStream_t)stream);
+  e = (b->phase == 2) ? cudaSuccess : simt_render_bwd(*b, L, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_render_bwd");
 }
 
@@ -238,6 +240,48 @@ int nnb_refstage(const nnb_refstage_args* a, void* stream) {
   if (!a->workspace || a->workspace_bytes < refstage_workspace_bytes(a->h_d, a->w_d, a->pc_ratio)) return fail(-4, "nnb_refstage: workspace too small");
   cudaError_t e = launch_refstage(*a, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_refstage");
+}
+
+int nnb_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle_out[64]) {
+  if (!dev_ptr || !handle_out || bytes == 0) return fail(-3, "nnb_ipc_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "nnb_ipc_alloc: cudaMalloc");
+  e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "nnb_ipc_alloc: cudaIpcGetMemHandle"); }
+  memcpy(handle_out, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+int nnb_ipc_open(const unsigned char handle[64], void** peer_ptr) {
+  if (!handle || !peer_ptr) return fail(-3, "nnb_ipc_open: bad arguments");
+  cudaIpcMemHandle_t h; memcpy(&h, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_ipc_open");
+}
+int nnb_ipc_close(void* peer_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_ipc_close");
+}
+int nnb_ipc_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_ipc_free");
+}
+int nnb_allreduce_adam(const nnb_allreduce_adam_args* a, void* stream) {
+  if (!a) return fail(-1, "null args");
+  if (a->world < 1 || a->world > NNB_MAX_RANKS || a->rank < 0 || a->rank >= a->world || a->n_total <= 0 || (a->n_total & 3) || a->nsegs < 0 || a->nsegs > 8)
+    return fail(-2, "nnb_allreduce_adam: bad sizes");
+  for (int r = 0; r < a->world; ++r) if (!a->peer_grads[r] || !a->peer_flags[r]) return fail(-3, "nnb_allreduce_adam: null peer pointer");
+  for (int q = 0; q < a->nsegs; ++q) {
+    const nnb_adam_seg& s = a->segs[q];
+    if (!s.p || !s.m || !s.v || !s.lr_dev || !s.step_dev || s.offset < 0 || s.count <= 0 || s.offset + s.count > a->n_total)
+      return fail(-3, "nnb_allreduce_adam: bad segment");
+  }
+  cudaError_t e = launch_allreduce_adam(*a, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nnb_allreduce_adam");
 }
 
 int nnb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float b1, float b2, float eps,

@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
     const float* w = a.weights;
     for (int i = threadIdx.x; i < BIAS_FLOATS; i += blockDim.x) {
       float v;
-      if (i < 2048) v = __ldg(w + nnb::b_off(i >> 8) + (i & 255));
-      else if (i < 2304) v = __ldg(w + nnb::B_FEAT + (i - 2048));
+      if (i < 2048) v = -__ldg(w + nnb::b_off(i >> 8) + (i & 255));       // trunk / feature biases are stored NEGATED (epi_chunk32)
+      else if (i < 2304) v = -__ldg(w + nnb::B_FEAT + (i - 2048));
       else if (i < 2560) v = __ldg(w + nnb::W_SIG + (i - 2304));
       else if (i < 2944) v = __ldg(w + nnb::W_RGB + (i - 2560));
       else if (i == 2944) v = __ldg(w + nnb::B_SIG);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           float acc = __ldg(w + nnb::B_RGBH + row);
 #pragma unroll
           for (int k = 0; k < 27; ++k) acc = fmaf(__ldg(w + nnb::W_RGBH + (size_t)row * 283 + 256 + k), s_rayb[512 + r * 32 + k], acc);
-          s_rayb[r * 128 + row] = acc;
+          s_rayb[r * 128 + row] = -acc;            // negated like the other biases
         }
       }
       fence_async_smem();
@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         // than the 4 K-steps (~1.5k cycles) the tensor core spends on a block, so (2) never starves the MMA warp.
         const bool two_pass = (dbg & 8) != 0;    // experiment knob: re-read the accumulator in a second pass (round-1 layout)
         const bool need2 = (g == 7) || (g == 9) || stash;
-        auto side_work = [&](int cb, const float* v) {
+        const bool x_lo = !(dbg & 4);            // X planes carry the bf16 lo half too (NNB_DBG_FWD bit 2: hi only, experiment)
+        auto side_work = [&](int cb, const float* v, uint32_t mw) {
           if (g == 7) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) s_logit = fmaf(v[j], s_bias[2304 + cb * 32 + j], s_logit);
@@ -370,17 +371,13 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             for (int j4 = 0; j4 < 8; ++j4)
               __stcs(reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4), make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
           }
-          if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi|lo, coalesced 512 B per warp
+          if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi[|lo], coalesced 512 B per warp
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
-              split_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024);
+              plane_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024, x_lo);
           }
-          if (planes && (g < 8 || g == 9) && !(dbg & 2)) {   // ReLU bitmask of this 32-column chunk (g = 9: rgb hidden layer, slot 8)
-            uint32_t mw = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mw |= min(__float_as_uint(v[j]), 1u) << j;   // v = max(x, 0): v > 0 <=> its bits are non-zero
-            __stcs(st.mask + ((size_t)(g < 8 ? g : 8) * st.Mpad + m) * 8 + cb, mw);
-          }
+          if (planes && (g < 8 || g == 9) && !(dbg & 2))     // ReLU gate bits of this 32-column chunk (g = 9: rgb hidden layer, slot 8);
+            __stcs(st.mask + ((size_t)(g < 8 ? g : 8) * st.Mpad + m) * 8 + cb, mw);   // column j at bit 31 - j (epi_chunk32)
         };
 #pragma unroll 1
         for (int ci = 0; ci < nch; ++ci) {
@@ -389,24 +386,16 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           tc_ld32(lane_addr + buf * 256 + cb * 32, r);
           PROF_ADD(2);
           float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
-            v[j] = (g == 8) ? x : fmaxf(x, 0.f);
-          }
+          const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, true)
+                                       : epi_chunk32<true>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, g < 9);
           if (g < 9) {
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) {
-              const int kblock = cb * 4 + kb;
-              split_store8(v + kb * 8, A_hi + kblock * 2048 + row * 16, A_lo + kblock * 2048 + row * 16);
-            }
             PROF_ADD(3);
             fence_async_smem();
             PROF_ADD(4);
             mbar_arrive(BAR(B_AREADY + ci));     // 256 arrivals (both halves) complete block ci
             PROF_ADD(5);
           }
-          if (need2 && !two_pass) side_work(cb, v);
+          if (need2 && !two_pass) side_work(cb, v, mw);
         }
         if (need2 && two_pass) {
 #pragma unroll 1
@@ -415,12 +404,9 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             uint32_t r[32];
             tc_ld32(lane_addr + buf * 256 + cb * 32, r);
             float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]) + bias[cb * 32 + j];
-              v[j] = (g == 8) ? x : fmaxf(x, 0.f);
-            }
-            side_work(cb, v);
+            const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, nullptr, nullptr, false)
+                                         : epi_chunk32<true>(r, bias + cb * 32, v, nullptr, nullptr, false);
+            side_work(cb, v, mw);
           }
         }
         tc_fence_before();
@@ -551,5 +537,5 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
 // data/weight-gradient kernels consume it directly (a tcgen05 backward replaces this next).
 cudaError_t tc_render_bwd(const nnb_render_bwd_args& b, const WsLayout& L, cudaStream_t st) {
   if (b.fwd.flags & NNB_TCBWD) return tc_render_bwd_planes(b, L, L.total + align_up(IMG_BYTES, 256), st);
-  return simt_render_bwd(b, L, st);
+  return b.phase == 2 ? cudaSuccess : simt_render_bwd(b, L, st);
 }

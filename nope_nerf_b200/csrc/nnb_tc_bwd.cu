@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       const float4* rp = reinterpret_cast<const float4*>(P.rec + mn);
       const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
       rec_pf.r = r0.x; rec_pf.g = r0.y; rec_pf.b = r0.z; rec_pf.a = r0.w; rec_pf.s = r1.x; rec_pf.z = r1.y; rec_pf.pad0 = r1.z; rec_pf.pad1 = r1.w;
-      hm_pf = __ldg(reinterpret_cast<const uint4*>(P.mask + ((size_t)8 * P.Mpad + mn) * 8));   // sign bits of the rgb hidden layer
+      hm_pf = __ldg(reinterpret_cast<const uint4*>(P.mask + ((size_t)8 * P.Mpad + mn) * 8));   // gate bits of the rgb hidden layer
+      hm_pf.x = __brev(hm_pf.x); hm_pf.y = __brev(hm_pf.y); hm_pf.z = __brev(hm_pf.z); hm_pf.w = __brev(hm_pf.w);   // stored MSB-first (epi_chunk32)
     };
     if ((int)blockIdx.x < n_tiles) prefetch_rows(blockIdx.x);
     for (int tt = 0; tt < my_tiles; ++tt) {
@@ -309,7 +310,9 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         const uint32_t* mrow = (mask_l >= 0) ? P.mask + ((size_t)mask_l * P.Mpad + m) * 8 : nullptr;
         // this thread's four mask words (chunks half, 2+half, 4+half, 6+half): loaded BEFORE the accumulator wait
         uint32_t mq0 = 0xffffffffu, mq1 = 0xffffffffu, mq2 = 0xffffffffu, mq3 = 0xffffffffu;
-        if (mrow) { mq0 = __ldg(mrow + half); mq1 = __ldg(mrow + 2 + half); mq2 = __ldg(mrow + 4 + half); mq3 = __ldg(mrow + 6 + half); }
+        if (mrow) {   // the forward stores column j of a chunk at bit 31 - j
+          mq0 = __brev(__ldg(mrow + half)); mq1 = __brev(__ldg(mrow + 2 + half)); mq2 = __brev(__ldg(mrow + 4 + half)); mq3 = __brev(__ldg(mrow + 6 + half));
+        }
         mbar_wait(BAR(D_ACCFULL + buf), use & 1u);
         tc_fence_after();
         const int nch = (pos == 5 || pos == 10) ? 1 : 4;   // 32-column chunks handled by this half
@@ -416,7 +419,7 @@ struct WgJob {
   int cost;                                          // bytes-per-tile weight used to balance the CTA pairs
 };
 constexpr int MAX_WG_JOBS = 12;
-struct WgJobs { WgJob j[MAX_WG_JOBS]; int njobs, n_tiles; };
+struct WgJobs { WgJob j[MAX_WG_JOBS]; int njobs, n_tiles, x_lo; };   // x_lo = 0: activation planes carry the bf16 hi half only
 
 constexpr int WG_SET = 98304;                        // one half-tile operand set: A_hi 16K | A_lo 16K | B_hi 32K | B_lo 32K
 constexpr int WG_AHI = 0, WG_ALO = 16384, WG_BHI = 32768, WG_BLO = 65536;
@@ -510,6 +513,7 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               mbar_wait(BAR(G_EMPTY + set * 4 + bi[c]), ph);
+              if (c == 2 && !jobs.x_lo) { mbar_expect_tx(BAR(G_FULL + set * 4 + bi[c]), 0); continue; }   // no lo plane: keep the barrier protocol
               mbar_expect_tx(BAR(G_FULL + set * 4 + bi[c]), nb[c]);
               bulk_g2s(sb + dsto[c], src[c], nb[c], BAR(G_FULL + set * 4 + bi[c]));
             }
@@ -556,9 +560,11 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
             if (!ok[3]) mbar_wait(BAR(G_FULL + set * 4 + 3), ph);
             tc_fence_after();
             DGP_ADD(0);
+            if (jobs.x_lo) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              tc_mma_f16(tmem_base, make_desc(sb + WG_AHI + ks * 256, 128, 1024), make_desc(sb + WG_BLO + ks * 256, 128, 1024), idesc, 1u);
+              for (int ks = 0; ks < 4; ++ks)
+                tc_mma_f16(tmem_base, make_desc(sb + WG_AHI + ks * 256, 128, 1024), make_desc(sb + WG_BLO + ks * 256, 128, 1024), idesc, 1u);
+            }
             tc_commit(BAR(G_EMPTY + set * 4 + 0)); tc_commit(BAR(G_EMPTY + set * 4 + 3));
             DGP_SKIP();
             if (!ok[1]) mbar_wait(BAR(G_FULL + set * 4 + 1), ph);
@@ -776,6 +782,9 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   float4* gv = reinterpret_cast<float4*>(base + L.gv);
   unsigned char* img_t = reinterpret_cast<unsigned char*>(base + img_t_offset);
   unsigned int* gmax = reinterpret_cast<unsigned int*>(base + L.gmax);
+  const bool do1 = b.phase != 2, do2 = b.phase != 1;
+  const int n_tiles = (int)L.n_tiles;
+  if (do1) {
   e = cudaMemsetAsync(gmax, 0, 4, st);
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
@@ -789,7 +798,6 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   P.mask = reinterpret_cast<const uint32_t*>(base + L.mask);
   for (int i = 0; i < 10; ++i) P.dyp[i] = reinterpret_cast<unsigned char*>(base + L.dyp[i]);
   P.Mpad = L.Mpad; P.gmax = gmax; P.g_weights = b.g_weights;
-  const int n_tiles = (int)L.n_tiles;
   const int write_dy = b.g_weights ? 1 : 0;
   const int CL = cluster_size_option();
   int grid_d = n_tiles < n_sm ? n_tiles : n_sm;
@@ -799,6 +807,8 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   else e = launch_clustered(tc_dgrad<true, 1>, grid_d, 320, DG_TOTAL, 1, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
+  }
+  if (!do2) return cudaSuccess;
   // fork: the streaming head / direction reductions (fp32 side stashes) run beside tc_wgrad on a second stream
   static cudaStream_t aux = nullptr;
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -833,6 +843,7 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
     add(8, 256, 8, 256, nnb::W_FEAT, 256, 256, 1, 54);                                       // fc_feature: X = h7 = xp[8]
     add(9, 128, 9, 256, nnb::W_RGBH, 283, 256, 0, 27);                                       // rgb_layers.0[:, :256]: X = feat; the pair splits the tiles
     J.njobs = nj; J.n_tiles = n_tiles;
+    { static const int xlo = [] { const char* v = getenv("NNB_DBG_FWD"); return (v && (atoi(v) & 4)) ? 0 : 1; }(); J.x_lo = xlo; }
     const int grid_w = n_sm >= 2 ? (n_sm / 2) * 2 : 2;
     tc_wgrad<true><<<grid_w, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);
     e = cudaGetLastError();

@@ -79,6 +79,74 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot) ----
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ unsigned long long u2_pack(uint32_t a, uint32_t b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// Epilogue of one 32-column accumulator chunk of the forward chain, in ONE pass over the registers:
+//   nx = (-bias) - acc            (packed; `nbias` holds the NEGATED biases, so nx = -(acc + bias) bit for bit)
+//   v  = relu ? max(-nx, 0) : -nx (negation is a free operand modifier)
+//   gate bit = sign(nx)           (x > 0  <=>  nx < 0), shifted into `mw` MSB-first: column j ends up at bit 31 - j
+//   fp16 hi | lo split of v       (x = hi + lo to ~2^-22), written as the next layer's A operand (8 x 16 B per half)
+template <bool RELU>
+__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* nbias, float* v, unsigned char* hi_dst, unsigned char* lo_dst, bool write_a) {
+  uint32_t mw = 0;
+  const ulonglong2* nb = reinterpret_cast<const ulonglong2*>(nbias);
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      const ulonglong2 b4 = nb[kb * 2 + (i >> 1)];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = kb * 8 + (i + h) * 2;
+        const unsigned long long nx2 = f2_sub(h ? b4.y : b4.x, u2_pack(r[j], r[j + 1]));
+        float n0, n1; f2_unpack(nx2, n0, n1);
+        if (RELU) {
+          mw = __funnelshift_l(__float_as_uint(n0), mw, 1); mw = __funnelshift_l(__float_as_uint(n1), mw, 1);
+          v[j] = fmaxf(-n0, 0.f); v[j + 1] = fmaxf(-n1, 0.f);
+        } else { v[j] = -n0; v[j + 1] = -n1; }
+        if (write_a) {
+          __half2 hh = __floats2half2_rn(v[j], v[j + 1]);
+          const float2 hf = __half22float2(hh);
+          float l0, l1; f2_unpack(f2_sub(f2_pack(v[j], v[j + 1]), f2_pack(hf.x, hf.y)), l0, l1);
+          __half2 ll = __floats2half2_rn(l0, l1);
+          hi[i + h] = *reinterpret_cast<uint32_t*>(&hh); lo[i + h] = *reinterpret_cast<uint32_t*>(&ll);
+        }
+      }
+    }
+    if (write_a) {
+      *reinterpret_cast<uint4*>(hi_dst + kb * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(lo_dst + kb * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  return mw;
+}
+// bf16 hi (and optionally lo) operand plane of 8 values, streamed to global memory
+__device__ __forceinline__ void plane_stream8_bf16(const float* v, unsigned char* hi_dst, unsigned char* lo_dst, bool with_lo) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<uint32_t*>(&hh);
+    hi[i] = hb;
+    if (with_lo) {
+      float l0, l1;
+      f2_unpack(f2_sub(f2_pack(v[2 * i], v[2 * i + 1]), u2_pack(hb << 16, hb & 0xffff0000u)), l0, l1);   // bf16 -> f32 is a shift
+      __nv_bfloat162 ll = __floats2bfloat162_rn(l0, l1);
+      lo[i] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+  }
+  st_stream16(hi_dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+  if (with_lo) st_stream16(lo_dst, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

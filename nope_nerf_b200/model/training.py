@@ -173,8 +173,14 @@ class _GraphStep:
         dev = tr.device
         self.h, self.w, self.hd, self.wd = h, w, hd, wd
         self.rgb_l2, self.use_ref = bool(rgb_l2), bool(use_ref)
-        self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.imgpp = torch.zeros(2, dtype=torch.int64, device=dev)        # frame pointers {current, reference}
+        # per-step host scalars travel as ONE 32-byte asynchronous copy from a ring of page-locked slots:
+        # meta = int64 [camera index, reference camera index, frame pointer, reference frame pointer]
+        self.meta = torch.zeros(4, dtype=torch.int64, device=dev)
+        m32 = self.meta.view(torch.int32)
+        self.idx = m32[0:1]; self.idx_ref = m32[2:3]
+        self.imgpp = self.meta[2:4]                                       # frame pointers {current, reference}
+        self.meta_host = torch.zeros(16, 4, dtype=torch.int64).pin_memory(); self.meta_np = self.meta_host.numpy()
+        self.meta_ev = [None] * 16
         self.dpt = torch.zeros(hd, wd, device=dev)
         self.cam = torch.zeros(4, 4, device=dev); self.cam_host = None
         self.ss = torch.zeros(2, device=dev)               # effective (scale, shift) of the current view
@@ -190,7 +196,6 @@ class _GraphStep:
         self.rs_losses = torch.zeros(2, device=dev)        # {loss_pc, loss_rgb_s} of the reference-image stage (full-loss steps)
         self.rs_total = torch.zeros(1, device=dev)
         if self.use_ref:
-            self.idx_ref = torch.zeros(1, dtype=torch.int32, device=dev)
             self.dpt_ref = torch.zeros(hd, wd, device=dev)
             self.c2w_ref = torch.zeros(4, 4, device=dev); self.ss_ref = torch.zeros(2, device=dev)
             nbytes = L.lib.nnb_refstage_workspace_bytes(hd, wd, int(tr.pc_ratio))
@@ -212,7 +217,27 @@ class _GraphStep:
         return all(fa.ok for fa in self._adams())
 
     def body(self):
-        self.body_a(); self.reduce(); self.body_b()
+        self.body_a()
+        if self.tr._peer is not None:
+            self.body_peer()
+        else:
+            self.reduce(); self.body_b()
+
+    def body_peer(self):
+        """data parallel: all-reduce of the flat gradient buffer over NVLink peer memory fused with the three Adam updates"""
+        tr = self.tr
+        net = tr.model.renderer.model; pose, dnet = tr.pose_param_net, tr.distortion_net
+        V = pose.num_cams; o = L.NUM_PARAMS
+        ops.counter_incr(self.steps)
+        fa_m, fa_p, fa_d = self._adams()
+        gm = tr.optimizer.param_groups[0]; b1, b2 = gm['betas']
+        segs = [(net.flat_weights(), fa_m.m, fa_m.v, 0, o, self.lrs[0:1], self.steps[0:1], b1, b2, gm['eps'])]
+        gp = tr.optimizer_pose.param_groups[0]; gd = tr.optimizer_distortion.param_groups[0]
+        for prm, off, cnt, fa, g_, k in ((pose.r, o, 3 * V, fa_p, gp, 1), (pose.t, o + 3 * V, 3 * V, fa_p, gp, 1),
+                                         (dnet.global_scales, o + 6 * V, V, fa_d, gd, 2), (dnet.global_shifts, o + 7 * V, V, fa_d, gd, 2)):
+            if prm.requires_grad and id(prm) in fa.m:
+                segs.append((prm.data, fa.m[id(prm)], fa.v[id(prm)], off, cnt, self.lrs[k:k + 1], self.steps[k:k + 1], g_['betas'][0], g_['betas'][1], g_['eps']))
+        tr._peer.allreduce_adam(segs)
 
     def body_a(self):
         """everything up to the local gradients"""
@@ -220,26 +245,13 @@ class _GraphStep:
         pose, dnet = tr.pose_param_net, tr.distortion_net
         net = tr.model.renderer.model; rend = tr.model.renderer
         h, w = self.h, self.w
-        gbuf, gv = tr._grad_buffer()
+        gbuf, gv = tr._grad_buffer(peer_step=True)
         self.small.zero_()
         g_c2w = self.small[:16].view(4, 4); g_ss = self.small[16:18]
         ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx, dnet.fix_scaleN, self.ss)
         init = None if pose.init_c2w is None else pose.init_c2w.detach()
         ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx, self.c2w)
         gs = 1.0 / tr.world
-        if self.use_ref:
-            # reference-image stage on a forked stream: it only needs the two poses / distortions / frames, and accumulates its
-            # pose / distortion gradients (atomics) into the buffers the render backward also accumulates into
-            cur = torch.cuda.current_stream()
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
-                ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx_ref, self.c2w_ref)
-                ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx_ref, dnet.fix_scaleN, self.ss_ref)
-                self.rs_total.zero_()
-                ops.refstage_raw(self.c2w, self.ss, self.c2w_ref, self.ss_ref, self.dpt, self.dpt_ref, H=h, W=w, img_pp=self.imgpp, cam=self.cam,
-                                 cam_idx_dev=self.idx, num_cams=pose.num_cams, weights_dev=self.wts[2:4], nearest_limit=tr.nearest_limit,
-                                 pc_ratio=tr.pc_ratio, scale_pcs=tr.scale_pcs, detach_rgbs_scale=tr.detach_rgbs_scale, shift_first=tr.shift_first,
-                                 losses=self.rs_losses, g_c2w=g_c2w, g_dist=g_ss, loss_total=self.rs_total, grad_scale=gs, workspace=self.rs_ws)
         n_points = tr.n_training_points
         if tr.pixel_sampler == 'randperm' or (tr.pixel_sampler == 'auto' and not tr.use_cuda_graph) or n_points > min(h * w // 2, 8192):
             ray_idx = torch.randperm(h * w, device=dev)[:n_points]                # training.py:257 (reference RNG stream)
@@ -263,10 +275,28 @@ class _GraphStep:
                                     ray_idx, h * w, self.out4, self.g_rgb, self.g_dp, self.g_dg, grad_scale=gs, w_dev=self.wts)
         ws = call.ws
         call.pooled = False                                 # memory referenced by a captured graph never returns to the pool
-        call.backward(self.g_rgb, self.g_dp, None if tr.detach_gt_depth else self.g_dg, gbuf[:L.NUM_PARAMS], g_c2w, None, None, g_ss)
+        bw = (self.g_rgb, self.g_dp, None if tr.detach_gt_depth else self.g_dg, gbuf[:L.NUM_PARAMS], g_c2w, None, None, g_ss)
+        if not self.use_ref:
+            call.backward(*bw)
+        else:
+            # The reference-image stage only needs the two poses / distortions / frames.  It is forked beside the weight-gradient
+            # kernel of the render backward: tc_wgrad sits on the HBM roofline with the SIMT pipes idle (192 threads, 108 registers per
+            # SM), so the brute-force chamfer's blocks run in its shadow; its pose / distortion gradients accumulate (atomics) into the
+            # buffers the render backward also accumulates into.
+            call.backward(*bw, phase=1)
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            call.backward(*bw, phase=2)
+            with torch.cuda.stream(self.side):
+                ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx_ref, self.c2w_ref)
+                ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx_ref, dnet.fix_scaleN, self.ss_ref)
+                self.rs_total.zero_()
+                ops.refstage_raw(self.c2w, self.ss, self.c2w_ref, self.ss_ref, self.dpt, self.dpt_ref, H=h, W=w, img_pp=self.imgpp, cam=self.cam,
+                                 cam_idx_dev=self.idx, num_cams=pose.num_cams, weights_dev=self.wts[2:4], nearest_limit=tr.nearest_limit,
+                                 pc_ratio=tr.pc_ratio, scale_pcs=tr.scale_pcs, detach_rgbs_scale=tr.detach_rgbs_scale, shift_first=tr.shift_first,
+                                 losses=self.rs_losses, g_c2w=g_c2w, g_dist=g_ss, loss_total=self.rs_total, grad_scale=gs, workspace=self.rs_ws)
+            cur.wait_stream(self.side)
         self.keep.append((call, ws, ray_idx, noise))        # graph-owned memory stays referenced (and out of the workspace pool)
-        if self.use_ref:
-            torch.cuda.current_stream().wait_stream(self.side)
         ops.pose_bwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx, g_c2w,
                          gv['r'] if pose.r.requires_grad else None, gv['t'] if pose.t.requires_grad else None)
         ops.distortion_bwd_dev(dnet.global_scales.detach(), self.idx, dnet.fix_scaleN, g_ss,
@@ -313,17 +343,21 @@ class _GraphStep:
     def run(self, data, wts):
         tr = self.tr; dev = tr.device
         img, img_keep = self._frame_ptr(data.get('img'), 0)
-        ptrs = [img.data_ptr(), 0]
+        meta = [int(data.get('img.idx')), 0, img.data_ptr(), 0]
         keep = [img_keep]
-        self.idx.fill_(int(data.get('img.idx')))
         self.dpt.copy_(data.get('img.dpt').reshape(self.hd, self.wd), non_blocking=True)
         if self.use_ref:
             ref, ref_keep = self._frame_ptr(data.get('img.ref_imgs'), 1)
-            ptrs[1] = ref.data_ptr(); keep.append(ref_keep)
-            self.idx_ref.fill_(int(data.get('img.ref_idxs')))
+            meta[3] = ref.data_ptr(); keep.append(ref_keep)
+            meta[1] = int(data.get('img.ref_idxs'))
             self.dpt_ref.copy_(data.get('img.ref_dpts').reshape(self.hd, self.wd), non_blocking=True)
-        if getattr(self, 'ptrs_host', None) != ptrs:
-            self.imgpp.copy_(torch.tensor(ptrs, dtype=torch.int64)); self.ptrs_host = ptrs
+        if getattr(self, 'meta_last', None) != meta:
+            k = self.calls % 16
+            if self.meta_ev[k] is not None: self.meta_ev[k].synchronize()   # the slot's previous copy has run (16 steps ago)
+            self.meta_np[k] = meta
+            self.meta.copy_(self.meta_host[k], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(); self.meta_ev[k] = ev
+            self.meta_last = meta
         self.dev_refs = keep
         cm = data.get('img.camera_mat')
         if self.cam_host is None or (cm.device.type == 'cpu' and not torch.equal(cm.reshape(4, 4), self.cam_host)):
@@ -354,7 +388,7 @@ class _GraphStep:
                 # world == 1: one graph for the whole step.  world > 1: the NCCL all-reduce stays an eager call between two
                 # graphs (gradients | optimizers); thread_local because the NCCL watchdog thread touches the CUDA API
                 self.graph = torch.cuda.CUDAGraph(keep_graph=True) if tr.keep_graph else torch.cuda.CUDAGraph()
-                if tr.world == 1:
+                if tr.world == 1 or tr._peer is not None:      # peer exchange: the collective is one of the graph's kernels
                     with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                         self.body()
                 else:
@@ -364,7 +398,7 @@ class _GraphStep:
                     with torch.cuda.graph(self.graph_b, capture_error_mode="thread_local"):
                         self.body_b()
             self.graph.replay()
-            if tr.world > 1:
+            if tr.world > 1 and tr._peer is None:
                 self.reduce()
                 self.graph_b.replay()
         for fa in fas:
@@ -379,7 +413,7 @@ class _GraphStep:
                 self.host_refs.pop(0)
         # per-call snapshot (ONE small kernel): later steps overwrite the persistent buffers the graph writes to, and train.py
         # keeps loss_dict['scale'/'shift'] per view (train.py:215-216)
-        snap = torch.cat([tr._gbuf[-4:], self.ss, self.rs_losses])
+        snap = torch.cat([(tr._peer.reduced if tr._peer is not None else tr._gbuf)[-4:], self.ss, self.rs_losses])
         zero = snap.new_zeros(())
         return {'loss': snap[0], 'loss_rgb': snap[1], 'loss_depth': snap[2], 'l2_mean': snap[3],
                 'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': snap[6] if wts[2] != 0.0 else zero,
@@ -432,6 +466,10 @@ class Trainer(object):
             raise ValueError("dp_mode='rays': training.n_training_points (%d) must be a multiple of the world size (%d): every rank "
                              "takes ray_idx[rank::world] and the loss normalisation assumes equal shards" % (self.n_training_points, self.world))
         self._gbuf = None
+        self._peer = None
+        # data-parallel exchange: ONE kernel over NVLink peer memory (all-reduce fused with the Adam updates, captured in the step
+        # graph); peer_exchange=False / NNB_PEER_EXCHANGE=0 falls back to torch.distributed.all_reduce between two graphs
+        self.peer_exchange = bool(kwargs.get('peer_exchange', os.environ.get('NNB_PEER_EXCHANGE', '1') == '1'))
         self._pix_cache = {}
         # fused flat-buffer Adam; optimizers remain the caller's objects
         self.fused_adam = kwargs.get('fused_adam', True)
@@ -447,28 +485,44 @@ class Trainer(object):
         self.pixel_sampler = kwargs.get('pixel_sampler', 'auto')
 
     # ------------------------------------------------------------------------------------
-    def _grad_buffer(self):
-        """[MLP 595844 | r 3V | t 3V | scales V | shifts V | loss scalars 4], zeroed, installed as .grad."""
+    def _grad_buffer(self, peer_step=False):
+        """[MLP 595844 | r 3V | t 3V | scales V | shifts V | loss scalars 4], zeroed; the kernels accumulate into it.
+        Installed as every parameter's .grad -- except in a peer-exchange step (data parallel, nnb_allreduce_adam), where .grad
+        shows the buffer that receives the SUM over the ranks while the local contributions go to the IPC-shared buffer."""
         V = self.pose_param_net.num_cams if self.pose_param_net is not None else 0
         n = L.NUM_PARAMS + 8 * V + 4
         dev = self.device
         if self._gbuf is None or self._gbuf.numel() != n:
-            self._gbuf = torch.zeros(n, device=dev)
+            if self.world > 1 and self.peer_exchange and torch.device(dev).type == 'cuda':
+                from ..peer import PeerGradExchange
+                self._peer = PeerGradExchange(n, dev, self.dp_group)
+                self._gbuf = self._peer.grad
+            else:
+                self._peer = None
+                self._gbuf = torch.zeros(n, device=dev)
         g = self._gbuf
         g.zero_()
         o = L.NUM_PARAMS
         net = self.model.renderer.model
-        net.flat_grad(zero=False, alias=g[:o])
-        views = {}
+        shown = self._peer.reduced if (peer_step and self._peer is not None) else g
+
+        def split(buf):
+            v = {}
+            if self.pose_param_net is not None:
+                v['r'] = buf[o:o + 3 * V].view(V, 3); v['t'] = buf[o + 3 * V:o + 6 * V].view(V, 3)
+            if self.distortion_net is not None:
+                v['scales'] = buf[o + 6 * V:o + 7 * V].view(V, 1); v['shifts'] = buf[o + 7 * V:o + 8 * V].view(V, 1)
+            v['losses'] = buf[n - 4:]
+            return v
+        views = split(g)
+        sv = views if shown is g else split(shown)
+        net.flat_grad(zero=False, alias=shown[:o])
         if self.pose_param_net is not None:
-            views['r'] = g[o:o + 3 * V].view(V, 3); views['t'] = g[o + 3 * V:o + 6 * V].view(V, 3)
-            if self.pose_param_net.r.requires_grad: self.pose_param_net.r.grad = views['r']
-            if self.pose_param_net.t.requires_grad: self.pose_param_net.t.grad = views['t']
+            if self.pose_param_net.r.requires_grad: self.pose_param_net.r.grad = sv['r']
+            if self.pose_param_net.t.requires_grad: self.pose_param_net.t.grad = sv['t']
         if self.distortion_net is not None:
-            views['scales'] = g[o + 6 * V:o + 7 * V].view(V, 1); views['shifts'] = g[o + 7 * V:o + 8 * V].view(V, 1)
-            if self.distortion_net.global_scales.requires_grad: self.distortion_net.global_scales.grad = views['scales']
-            if self.distortion_net.global_shifts.requires_grad: self.distortion_net.global_shifts.grad = views['shifts']
-        views['losses'] = g[n - 4:]
+            if self.distortion_net.global_scales.requires_grad: self.distortion_net.global_scales.grad = sv['scales']
+            if self.distortion_net.global_shifts.requires_grad: self.distortion_net.global_shifts.grad = sv['shifts']
         return g, views
 
     def train_step(self, data, it=None, epoch=None, scheduling_start=None, render_path=None):

@@ -134,18 +134,21 @@ class RenderCall:
             if self.pooled: _pool.give(self.ws)
             self.ws = None
 
-    def backward(self, g_rgb, g_depth_pred, g_depth_gt, g_weights, g_c2w, g_cam=None, g_depth=None, g_scale_shift=None):
-        """all outputs are accumulated into (caller-zeroed) buffers; g_weights may be None (pose only)."""
+    def backward(self, g_rgb, g_depth_pred, g_depth_gt, g_weights, g_c2w, g_cam=None, g_depth=None, g_scale_shift=None, phase=0):
+        """all outputs are accumulated into (caller-zeroed) buffers; g_weights may be None (pose only).  phase 1 / 2: the two halves
+        of the tcgen05 backward (data gradients | weight gradients + ray adjoint), see include/nope_nerf_b200.h."""
         if self.ws is None:
             raise RuntimeError("backward called without a stashed forward")
         b = L.RenderBwdArgs()
+        b.phase = int(phase)
         b.fwd = self.args
         keep = [_f32c(g_rgb), _f32c(g_depth_pred), _f32c(g_depth_gt)]
         b.g_rgb, b.g_depth_pred, b.g_depth_gt = L.ptr(keep[0]), L.ptr(keep[1]), L.ptr(keep[2])
         b.g_weights = L.ptr(g_weights); b.g_c2w = L.ptr(g_c2w); b.g_cam = L.ptr(g_cam); b.g_depth = L.ptr(g_depth)
         b.g_scale_shift = L.ptr(g_scale_shift)
         L.check(L.lib.nnb_render_bwd(C.byref(b), _stream()), "nnb_render_bwd")
-        self.release()
+        if phase != 1:
+            self.release()
 
 
 class _RenderFn(torch.autograd.Function):
