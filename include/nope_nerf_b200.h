@@ -33,6 +33,11 @@ extern "C" {
 #define NNB_SHIFT_FIRST 128u /* training.shift_first    (training.py:241-245)                     */
 #define NNB_STASH 256u      /* keep activations in the workspace for nnb_render_bwd               */
 #define NNB_TCBWD 512u      /* NNB_ENGINE_TC only: tcgen05 backward (operand-image stash) instead of the fp32 one */
+#define NNB_WG16 1024u      /* with NNB_TCBWD: the weight-gradient GEMMs dW = dY^T X read ONE fp16 plane per operand (X = the hi
+                             * half of the forward's fp16 hi|lo operand, dY = fp16 of dY * 2^k with a per-layer power-of-two scale
+                             * taken from the previous step's max |dY|, "delayed scaling") instead of bf16 hi|lo planes: half the
+                             * stash traffic, a third of the MMAs; MLP weight gradients then carry fp16 operand rounding
+                             * (~3e-4 relative, unbiased), everything else (outputs, pose / distortion / bias gradients) is unchanged */
 
 /* engines */
 #define NNB_ENGINE_SIMT 0 /* exact fp32 FMA path                                        */
@@ -85,6 +90,12 @@ typedef struct nnb_render_bwd_args {
    * reference-image stage) beside the HBM-bound weight-gradient kernel: 1 = compositing adjoint + data-gradient chain,
    * 2 = weight gradients + ray adjoint.  Other engines do everything in phase 1 (or 0) and nothing in phase 2. */
   uint32_t phase;
+  /* NNB_WG16 only.  wg_state: 32 persistent device floats owned by the caller (zeroed once): [0..9] per-layer dY scales,
+   * [16..25] running max |dY| of the current step (uint bits).  wg_seed != 0 (the first step with this state): the data-gradient
+   * chain runs once more up front just to measure max |dY| (later steps reuse the previous step's maxima).  wg_state NULL:
+   * scratch state in the workspace, seeded on every call (stateless one-off calls, 2x the data-gradient time). */
+  float* wg_state;
+  uint32_t wg_seed;
 } nnb_render_bwd_args;
 
 const char* nnb_last_error(void);

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NNB_LIB_PATH") or os.path.join(HERE, "libnope_nerf_b200.so")   # NNB_LIB_PATH: instrumented debug builds
 
 NUM_PARAMS = 595844
-DIST_ALPHA, NDC, NORMALISE, USE_DIR, WHITE_BG, EVAL, SOFTPLUS, SHIFT_FIRST, STASH, TCBWD = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+DIST_ALPHA, NDC, NORMALISE, USE_DIR, WHITE_BG, EVAL, SOFTPLUS, SHIFT_FIRST, STASH, TCBWD, WG16 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
 ENGINE_SIMT, ENGINE_TC = 0, 1
 
 _f = C.c_void_p  # device pointers travel as integers
@@ -27,7 +27,8 @@ class RenderArgs(C.Structure):
 
 class RenderBwdArgs(C.Structure):
     _fields_ = [("fwd", RenderArgs), ("g_rgb", _f), ("g_depth_pred", _f), ("g_depth_gt", _f),
-                ("g_weights", _f), ("g_c2w", _f), ("g_cam", _f), ("g_depth", _f), ("g_scale_shift", _f), ("phase", C.c_uint32)]
+                ("g_weights", _f), ("g_c2w", _f), ("g_cam", _f), ("g_depth", _f), ("g_scale_shift", _f), ("phase", C.c_uint32),
+                ("wg_state", _f), ("wg_seed", C.c_uint32)]
 
 
 class RefStageArgs(C.Structure):

@@ -84,6 +84,7 @@ __device__ unsigned long long g_tcprof2[148][8];
 struct TcStash {   // fp32 [sample][feature] stash (layout of nnb_simt.cu) and, with NNB_TCBWD, operand planes + ReLU bitmasks
   float *h[8], *feat, *hr, *enc, *denc;
   unsigned char* xp[10]; uint32_t* mask; size_t Mpad; int tcb;
+  int wg16;   // NNB_WG16: X planes are ONE fp16 plane per tile (the hi words of the forward's own A / E operands)
 };
 
 __device__ __forceinline__ void row_geometry_tc(const nnb_render_args& a, size_t m, size_t M, Ray& ray, int& n, int& i, float& z, float p[3]) {
@@ -286,14 +287,18 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int kb = half * 4 + kk;
-          split_store8(ee + kk * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
+          const uint4 eh = split_store8_hi(ee + kk * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
           if (stash && !(st.tcb & 1)) {
             *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8) = make_float4(ee[kk * 8], ee[kk * 8 + 1], ee[kk * 8 + 2], ee[kk * 8 + 3]);
             *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8 + 4) = make_float4(ee[kk * 8 + 4], ee[kk * 8 + 5], ee[kk * 8 + 6], ee[kk * 8 + 7]);
           }
           if (stash && (st.tcb & 1)) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
-            unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + (row >> 6) * 8192 + (row & 63) * 16;   // [hi|lo][half][kb][64][8]
-            split_stream8_bf16(ee + kk * 8, dst + kb * 1024, dst + 16384 + kb * 1024);
+            if (st.wg16) {                 // ... or the fp16 hi half of the E operand itself: [half][kb][64][8], one plane
+              st_stream16(st.xp[0] + (size_t)tile * (PLANE_TILE_64 / 2) + (row >> 6) * 8192 + (row & 63) * 16 + kb * 1024, eh);
+            } else {
+              unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + (row >> 6) * 8192 + (row & 63) * 16;   // [hi|lo][half][kb][64][8]
+              split_stream8_bf16(ee + kk * 8, dst + kb * 1024, dst + 16384 + kb * 1024);
+            }
           }
         }
       }
@@ -343,16 +348,17 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
         const bool planes = stash && (st.tcb & 1);
         const int dbg = st.tcb >> 1;
-        unsigned char* xplane = (planes && g < 9 && !(dbg & 1)) ? st.xp[1 + g] + (size_t)tile * PLANE_TILE_256 + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
+        const bool wg16 = st.wg16 != 0;
+        unsigned char* xplane = (planes && g < 9 && !(dbg & 1)) ? st.xp[1 + g] + (size_t)tile * (wg16 ? PLANE_TILE_256 / 2 : PLANE_TILE_256) + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
         // Per 32-column chunk: (1) critical path of the MMA warp: accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand,
         // block by block (the two halves convert adjacent chunks of the SAME 64-column block, so block `ci` is complete
         // after one chunk time); (2) after the block is signalled, from the same registers, everything the next MMA does
         // not need: density / colour heads, fp32 side stash, bf16 operand planes, ReLU bitmasks.  One chunk takes less
         // than the 4 K-steps (~1.5k cycles) the tensor core spends on a block, so (2) never starves the MMA warp.
-        const bool two_pass = (dbg & 8) != 0;    // experiment knob: re-read the accumulator in a second pass (round-1 layout)
+        const bool two_pass = false;
         const bool need2 = (g == 7) || (g == 9) || stash;
         const bool x_lo = !(dbg & 4);            // X planes carry the bf16 lo half too (NNB_DBG_FWD bit 2: hi only, experiment)
-        auto side_work = [&](int cb, const float* v, uint32_t mw) {
+        auto side_work = [&](int cb, const float* v, uint32_t mw, const uint32_t* hw) {
           if (g == 7) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) s_logit = fmaf(v[j], s_bias[2304 + cb * 32 + j], s_logit);
@@ -371,7 +377,11 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             for (int j4 = 0; j4 < 8; ++j4)
               __stcs(reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4), make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
           }
-          if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi[|lo], coalesced 512 B per warp
+          if (xplane && wg16) {   // the fp16 hi words just written as the next A operand ARE the X plane: 4 x 16 B, no conversion
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+              st_stream16(xplane + (cb * 4 + kb) * 1024, make_uint4(hw[kb * 4], hw[kb * 4 + 1], hw[kb * 4 + 2], hw[kb * 4 + 3]));
+          } else if (xplane) {   // X operand plane of the weight-gradient pass (h_g, or feat for g = 8): bf16 hi[|lo], coalesced 512 B per warp
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
               plane_stream8_bf16(v + kb * 8, xplane + (cb * 4 + kb) * 1024, xplane + 65536 + (cb * 4 + kb) * 1024, x_lo);
@@ -386,8 +396,9 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           tc_ld32(lane_addr + buf * 256 + cb * 32, r);
           PROF_ADD(2);
           float v[32];
-          const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, true)
-                                       : epi_chunk32<true>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, g < 9);
+          uint32_t hw[16];
+          const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, true, hw)
+                                       : epi_chunk32<true>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, g < 9, hw);
           if (g < 9) {
             PROF_ADD(3);
             fence_async_smem();
@@ -395,19 +406,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             mbar_arrive(BAR(B_AREADY + ci));     // 256 arrivals (both halves) complete block ci
             PROF_ADD(5);
           }
-          if (need2 && !two_pass) side_work(cb, v, mw);
-        }
-        if (need2 && two_pass) {
-#pragma unroll 1
-          for (int ci = 0; ci < nch; ++ci) {
-            const int cb = 2 * ci + half;
-            uint32_t r[32];
-            tc_ld32(lane_addr + buf * 256 + cb * 32, r);
-            float v[32];
-            const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, nullptr, nullptr, false)
-                                         : epi_chunk32<true>(r, bias + cb * 32, v, nullptr, nullptr, false);
-            side_work(cb, v, mw);
-          }
+          if (need2 && !two_pass) side_work(cb, v, mw, hw);
         }
         tc_fence_before();
         mbar_arrive(BAR(B_ACCEMPTY + buf));
@@ -507,6 +506,7 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
   const int stash = (a.flags & NNB_STASH) ? 1 : 0;
   if (stash) {
     ts.tcb = (a.flags & NNB_TCBWD) ? 1 : 0;
+    ts.wg16 = (ts.tcb && (a.flags & NNB_WG16)) ? 1 : 0;
     if (ts.tcb) { const char* e = getenv("NNB_DBG_FWD"); if (e) ts.tcb |= atoi(e) << 1; }   // experiment knob (default off)
     for (int l = 0; l < 8; ++l) ts.h[l] = reinterpret_cast<float*>(base + L.h[l]);   // TCBWD: only h[7] is carved (others unused)
     ts.feat = reinterpret_cast<float*>(base + L.feat); ts.hr = reinterpret_cast<float*>(base + L.hr);

@@ -44,7 +44,8 @@ constexpr int DG_AHI = 0, DG_ALO = 65536, DG_W = 131072, DG_GENC = DG_W + NST * 
 constexpr int DG_SMALL = DG_GENC + 64 * 128 * 4;                                                   // 212992
 constexpr int DG_COLSUM = DG_SMALL + 640 * 4;     // bias gradients: column sums of dY, [9 layers][256] fp32
 constexpr int DG_BAR = DG_COLSUM + 9 * 256 * 4;
-constexpr int DG_TOTAL = DG_BAR + 32 * 8 + 16;
+constexpr int DG_WGS = DG_BAR + 32 * 8 + 16;          // NNB_WG16: float scale[10] | uint amax[10] (padded to 128 B)
+constexpr int DG_TOTAL = DG_WGS + 128;
 static_assert(DG_TOTAL <= 232448, "smem");
 enum { D_FULL = 0, D_EMPTY = NST, D_AREADY = 2 * NST, D_ACCFULL = 2 * NST + 4, D_ACCEMPTY = 2 * NST + 6 };
 
@@ -73,6 +74,7 @@ struct DgradPtrs {
   const unsigned int* gmax;                                  // max |g| bits -> power-of-two gradient scale
   float* g_weights;                                          // flat gradient (bias gradients are reduced here), or NULL
   size_t Mpad;
+  float* wg_state;                                           // NNB_WG16: [0..9] dY scales, [16..25] running max |dY| (uint bits); else NULL
 };
 
 // column sums over the 32 rows held by a warp: lane L ends up with sum_rows v[L]  (31 shuffles, butterfly transpose-reduce)
@@ -148,6 +150,10 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  float* s_wgscale = reinterpret_cast<float*>(smem + DG_WGS);                  // [10] power-of-two scales of the fp16 dY planes
+  unsigned int* s_amax = reinterpret_cast<unsigned int*>(smem + DG_WGS + 64);   // [10] max |dY| seen by this CTA (uint bits)
+  const bool wg16 = P.wg_state != nullptr;
+  if (threadIdx.x < 10) { s_wgscale[threadIdx.x] = wg16 ? P.wg_state[threadIdx.x] : 1.f; s_amax[threadIdx.x] = 0u; }
   for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) s_colsum[i] = 0.f;
   for (int i = threadIdx.x; i < 640; i += blockDim.x)
     s_small[i] = (i < 384) ? __ldg(a.weights + nnb::W_RGB + i) : __ldg(a.weights + nnb::W_SIG + (i - 384));
@@ -281,7 +287,9 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         float* dyr = P.dyr + m * 128;
         // dY operand planes of the weight-gradient pass ([hi|lo][sample half][feature block][64 samples][8] bf16) are
         // streamed from registers next to the shared-memory image (the bulk-copy engine stays free for the weight ring)
-        unsigned char* gpl = write_dy ? P.dyp[9] + (size_t)tile * PLANE_TILE_128 + (row >> 6) * 16384 + (row & 63) * 16 : nullptr;
+        unsigned char* gpl = (write_dy && !wg16) ? P.dyp[9] + (size_t)tile * PLANE_TILE_128 + (row >> 6) * 16384 + (row & 63) * 16 : nullptr;
+        unsigned char* gpl16 = (write_dy && wg16) ? P.dyp[9] + (size_t)tile * (PLANE_TILE_128 / 2) + (row >> 6) * 16384 + (row & 63) * 16 : nullptr;
+        const float sc9 = s_wgscale[9];
 #pragma unroll 1
         for (int ji = 0; ji < 8; ++ji) {
           const int jb = 2 * ji + half;       // halves interleave 8-column groups: 64-column block b is done after ji = 4b+3
@@ -294,6 +302,12 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
             v[j] = ((mb >> j) & 1u) ? x : 0.f;
           }
           split_store8_bf16_dual(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16, gpl ? gpl + jb * 1024 : nullptr, gpl + 32768 + jb * 1024);
+          if (gpl16) stream8_f16_scaled(v, sc9, gpl16 + jb * 1024);
+          if (wg16 && ji == 0) {   // max |dY| sample (one 8-column group per row is enough: the scale has 2^10 of headroom)
+            float mx = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))), fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
+            const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+            if (lane == 0) atomicMax(&s_amax[9], mb);
+          }
           *reinterpret_cast<float4*>(dyr + jb * 8) = make_float4(v[0] * inv_gscale, v[1] * inv_gscale, v[2] * inv_gscale, v[3] * inv_gscale);
           *reinterpret_cast<float4*>(dyr + jb * 8 + 4) = make_float4(v[4] * inv_gscale, v[5] * inv_gscale, v[6] * inv_gscale, v[7] * inv_gscale);
           if ((ji & 3) == 3) { fence_async_smem(); mbar_arrive(BAR(D_AREADY + (ji >> 2))); }   // block 0 / 1 of g_yr complete (256 arrivals)
@@ -318,7 +332,9 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         const int nch = (pos == 5 || pos == 10) ? 1 : 4;   // 32-column chunks handled by this half
         // A will hold: pos0 -> g_feat ; pos1 -> g_y7 ; pos2..4 -> g_y6..4 ; pos6 -> g_y3 ; pos7..9 -> g_y2..0
         const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
-        unsigned char* gpl = (write_dy && writes_a) ? P.dyp[di] + (size_t)tile * PLANE_TILE_256 + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
+        unsigned char* gpl = (write_dy && writes_a && !wg16) ? P.dyp[di] + (size_t)tile * PLANE_TILE_256 + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
+        unsigned char* gpl16 = (write_dy && writes_a && wg16) ? P.dyp[di] + (size_t)tile * (PLANE_TILE_256 / 2) + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
+        const float scd = s_wgscale[di];
 #pragma unroll 1
         for (int ci = 0; ci < nch; ++ci) {
           const int cb = (nch == 1) ? half : 2 * ci + half;    // halves share each 64-column block (ready after one chunk time)
@@ -344,6 +360,17 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
               split_store8_bf16_dual(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16,
                                      gpl ? gpl + (cb * 4 + kb) * 1024 : nullptr, gpl + 65536 + (cb * 4 + kb) * 1024);
             fence_async_smem(); mbar_arrive(BAR(D_AREADY + ci));
+            if (gpl16) {   // fp16 dY plane of the weight-gradient pass: after the MMA warp has been released
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) stream8_f16_scaled(v + kb * 8, scd, gpl16 + (cb * 4 + kb) * 1024);
+            }
+            if (wg16 && ci == 0) {   // max |dY_l| sample: this thread's first chunk (a quarter of the columns)
+              float mx = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+              const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+              if (lane == 0) atomicMax(&s_amax[di], mb);
+            }
             if (write_dy) {   // bias gradient of this layer: db[n] = sum_m dY[m][n] (off the MMA's critical path)
               const float cs = warp_colsum32(v, lane);
               atomicAdd(&s_colsum[di * 256 + cb * 32 + lane], cs * inv_gscale);
@@ -389,6 +416,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   }
   tc_fence_before();
   __syncthreads();
+  if (wg16 && threadIdx.x < 10 && s_amax[threadIdx.x]) atomicMax(reinterpret_cast<unsigned int*>(P.wg_state) + 16 + threadIdx.x, s_amax[threadIdx.x]);
   if (write_dy && P.g_weights) {   // flush this CTA's bias-gradient partial sums
     for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) {
       const int di = i >> 8, n = i & 255;
@@ -417,9 +445,10 @@ struct WgJob {
   int ldw, kvalid, w_off;                            // row stride / valid columns / float offset of dW in the flat gradient
   int paired;                                        // 1: the two CTAs of a pair take the two 128-row halves of dW; 0: they split the tiles
   int cost;                                          // bytes-per-tile weight used to balance the CTA pairs
+  int dyi;                                           // index of the dY plane (per-layer scale of the NNB_WG16 planes)
 };
 constexpr int MAX_WG_JOBS = 12;
-struct WgJobs { WgJob j[MAX_WG_JOBS]; int njobs, n_tiles, x_lo; };   // x_lo = 0: activation planes carry the bf16 hi half only
+struct WgJobs { WgJob j[MAX_WG_JOBS]; int njobs, n_tiles, x_lo; const float* wg_state; };   // x_lo = 0: activation planes carry the bf16 hi half only
 
 constexpr int WG_SET = 98304;                        // one half-tile operand set: A_hi 16K | A_lo 16K | B_hi 32K | B_lo 32K
 constexpr int WG_AHI = 0, WG_ALO = 16384, WG_BHI = 32768, WG_BLO = 65536;
@@ -639,6 +668,183 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// NNB_WG16 weight gradients: ONE fp16 plane per operand (X = hi half of the forward's operands, dY = fp16 of dY * 2^k),
+// one MMA per K-step.  48 KB per 64-sample half-tile (dY 16 KB | X 32 KB) streamed through a 4-deep ring: the kernel is a pure
+// HBM stream (1.34 GB at 1024 x 128), the tensor pipe idles ~3/4 of the time.  Accumulation / flush as in tc_wgrad; the flush
+// multiplies by 2^-k of the job's dY plane.
+// ---------------------------------------------------------------------------------------------------
+constexpr int W16_SET = 49152, W16_NSET = 4, W16_A = 0, W16_B = 16384;
+constexpr int W16_XPOSE = W16_NSET * W16_SET;
+constexpr int W16_SEG = W16_XPOSE + 4 * 32 * 17 * 4;
+constexpr int W16_BAR = W16_SEG + 16 * 16;
+constexpr int W16_TOTAL = W16_BAR + 16 * 8 + 16;
+static_assert(W16_TOTAL <= 232448, "smem");
+enum { H_FULL = 0, H_EMPTY = W16_NSET, H_DONE = 2 * W16_NSET, H_DRAINED = 2 * W16_NSET + 1 };
+
+__global__ void __launch_bounds__(192, 1) tc_wgrad16(WgJobs jobs, float* __restrict__ gflat) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W16_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + W16_BAR + 16 * 8);
+  WgSeg* segs = reinterpret_cast<WgSeg*>(smem + W16_SEG);
+  __shared__ int s_nseg;
+  __shared__ float s_inv[10];
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int side = blockIdx.x & 1;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < W16_NSET; ++i) { mbar_init(BAR(H_FULL + i), 1); mbar_init(BAR(H_EMPTY + i), 1); }
+    mbar_init(BAR(H_DONE), 1); mbar_init(BAR(H_DRAINED), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const long long P = gridDim.x >> 1, p = blockIdx.x >> 1;
+    long long U = 0;
+    for (int j = 0; j < jobs.njobs; ++j) U += (long long)jobs.j[j].cost * jobs.n_tiles;
+    const long long lo = U * p / P, hi = U * (p + 1) / P;
+    long long u0 = 0;
+    int ns = 0;
+    for (int j = 0; j < jobs.njobs; ++j) {
+      const long long c = jobs.j[j].cost, u1 = u0 + c * jobs.n_tiles;
+      const long long a = lo > u0 ? lo : u0, b = hi < u1 ? hi : u1;
+      if (b > a) {
+        int t0 = (int)((a - u0 + c - 1) / c), t1 = (int)((b - u0 + c - 1) / c);
+        if (!jobs.j[j].paired) { const int mid = (t0 + t1) >> 1; if (side == 0) t1 = mid; else t0 = mid; }
+        if (t1 > t0 && ns < 16) { segs[ns].job = j; segs[ns].t0 = t0; segs[ns].t1 = t1; ++ns; }
+      }
+      u0 = u1;
+    }
+    s_nseg = ns;
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 42) { const float sc = jobs.wg_state[threadIdx.x - 32]; s_inv[threadIdx.x - 32] = sc > 0.f ? 1.f / sc : 1.f; }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nseg = s_nseg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;   // half-tile counter: ring slot = it % W16_NSET, barrier phase = (it / W16_NSET) & 1
+      for (int si = 0; si < nseg; ++si) {
+        const WgSeg sg = segs[si];
+        const WgJob& J = jobs.j[sg.job];
+        const int dy_half = J.dy_tile >> 1, x_half = J.x_tile >> 1;     // one plane per tile: [sample half][feature block][64][8] fp16
+        const int dy_off = (J.paired && J.dy_feat == 256) ? side * 16384 : 0;
+        for (int t = sg.t0; t < sg.t1; ++t) {
+          const unsigned char* dyt = J.dy + (size_t)t * J.dy_tile + dy_off;
+          const unsigned char* xt = J.x + (size_t)t * J.x_tile;
+#pragma unroll
+          for (int h = 0; h < 2; ++h, ++it) {
+            const int set = it % W16_NSET;
+            const uint32_t ph = ((it / W16_NSET) & 1u) ^ 1u, sb = smem_u32(smem + set * W16_SET);
+            mbar_wait(BAR(H_EMPTY + set), ph);
+            mbar_expect_tx(BAR(H_FULL + set), 16384 + x_half);
+            bulk_g2s(sb + W16_A, dyt + h * dy_half, 16384, BAR(H_FULL + set));
+            bulk_g2s(sb + W16_B, xt + h * x_half, x_half, BAR(H_FULL + set));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, gcount = 0;
+      for (int si = 0; si < nseg; ++si) {
+        const WgSeg sg = segs[si];
+        const WgJob& J = jobs.j[sg.job];
+        const uint32_t idesc = make_idesc_ex(128, J.N, 0, 0, 1, 1);     // fp16 x fp16, both MN-major
+        uint32_t acc = 0;
+        for (int t = sg.t0; t < sg.t1; ++t) {
+          if (acc == 0 && gcount > 0) { mbar_wait(BAR(H_DRAINED), (gcount - 1) & 1u); tc_fence_after(); }
+#pragma unroll
+          for (int h = 0; h < 2; ++h, ++it) {
+            const int set = it % W16_NSET;
+            const uint32_t ph = (it / W16_NSET) & 1u, sb = smem_u32(smem + set * W16_SET);
+            mbar_wait(BAR(H_FULL + set), ph);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_f16(tmem_base, make_desc(sb + W16_A + ks * 256, 128, 1024), make_desc(sb + W16_B + ks * 256, 128, 1024), idesc, acc | (uint32_t)(ks > 0));
+            acc = 1u;
+            tc_commit(BAR(H_EMPTY + set));
+          }
+          if (((t - sg.t0 + 1) % WG_GROUP) == 0 || t + 1 == sg.t1) { tc_commit(BAR(H_DONE)); ++gcount; acc = 0; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* xp = reinterpret_cast<float*>(smem + W16_XPOSE) + q * (32 * 17);
+    uint32_t gcount = 0;
+    for (int si = 0; si < nseg; ++si) {
+      const WgSeg sg = segs[si];
+      const WgJob& J = jobs.j[sg.job];
+      const float inv = s_inv[J.dyi];
+      const int n_base = (J.paired && J.dy_feat == 256) ? side * 128 : 0;
+      float* dst0 = gflat + J.w_off + (size_t)(n_base + q * 32) * J.ldw;
+      const int ngroups = (sg.t1 - sg.t0 + WG_GROUP - 1) / WG_GROUP, nchunks = J.N / 32;
+      for (int gi = 0; gi < ngroups; ++gi, ++gcount) {
+        mbar_wait(BAR(H_DONE), gcount & 1u);
+        tc_fence_after();
+        const bool last = (gi + 1 == ngroups);
+        for (int cb = 0; cb < nchunks; ++cb) {
+          uint32_t r[32];
+          tc_ld32(lane_addr + cb * 32, r);
+          if (gi > 0) {
+            uint32_t r2[32];
+            tc_ld32(lane_addr + 256 + cb * 32, r2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
+          if (!last) {
+            tc_st32(lane_addr + 256 + cb * 32, r);
+          } else {
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xp[lane * 17 + j] = __uint_as_float(r[hc * 16 + j]) * inv;
+              __syncwarp();
+              const int k = cb * 32 + hc * 16 + (lane & 15);
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) {
+                const int rw = rr + (lane >> 4);
+                if (k < J.kvalid) atomicAdd(dst0 + (size_t)rw * J.ldw + k, xp[rw * 17 + (lane & 15)]);
+              }
+              __syncwarp();
+            }
+          }
+        }
+        if (!last) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(BAR(H_DRAINED));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// NNB_WG16 delayed scaling: the max |dY_l| measured by the previous data-gradient pass becomes this pass's power-of-two scale
+// (max lands in [2^5, 2^6): 2^10 of headroom to fp16's 65504, 20 binades down to its smallest normal); the running maxima restart.
+__global__ void wg_scale_update_k(float* __restrict__ state) {
+  const int i = threadIdx.x;
+  if (i >= 10) return;
+  unsigned int* amax = reinterpret_cast<unsigned int*>(state) + 16;
+  const float m = __uint_as_float(amax[i]);
+  if (m > 0.f && isfinite(m)) { int e; frexpf(m, &e); state[i] = ldexpf(1.f, 6 - e); }
+  else if (!(state[i] > 0.f)) state[i] = 1.f;
+  amax[i] = 0u;
+}
+
 // per-ray view-direction gradient from the rgb hidden layer: g_v = encode_bwd( (sum_i g_yr_i) @ W_r[:,256:283] )
 // The direction encoding is constant along a ray, so both the per-ray view-direction gradient and the weight
 // gradient of rgb_layers.0[:, 256:283] only need G_ray[j] = sum_i g_yr[i][j]:
@@ -771,6 +977,8 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_TOTAL);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_wgrad16, cudaFuncAttributeMaxDynamicSharedMemorySize, W16_TOTAL);
+    if (e != cudaSuccess) return e;
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     attr = true;
@@ -784,6 +992,9 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   unsigned int* gmax = reinterpret_cast<unsigned int*>(base + L.gmax);
   const bool do1 = b.phase != 2, do2 = b.phase != 1;
   const int n_tiles = (int)L.n_tiles;
+  const bool wg16 = (a.flags & NNB_WG16) != 0 && b.g_weights != nullptr;
+  float* wg_state = wg16 ? (b.wg_state ? b.wg_state : reinterpret_cast<float*>(base + L.wgstate)) : nullptr;
+  const bool wg_seed = wg16 && (b.wg_seed != 0 || b.wg_state == nullptr);
   if (do1) {
   e = cudaMemsetAsync(gmax, 0, 4, st);
   if (e != cudaSuccess) return e;
@@ -797,14 +1008,25 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   P.hr = reinterpret_cast<const float*>(base + L.hr); P.dyr = reinterpret_cast<float*>(base + L.dyr);
   P.mask = reinterpret_cast<const uint32_t*>(base + L.mask);
   for (int i = 0; i < 10; ++i) P.dyp[i] = reinterpret_cast<unsigned char*>(base + L.dyp[i]);
-  P.Mpad = L.Mpad; P.gmax = gmax; P.g_weights = b.g_weights;
+  P.Mpad = L.Mpad; P.gmax = gmax; P.g_weights = b.g_weights; P.wg_state = wg_state;
   const int write_dy = b.g_weights ? 1 : 0;
   const int CL = cluster_size_option();
   int grid_d = n_tiles < n_sm ? n_tiles : n_sm;
   grid_d = (grid_d + CL - 1) / CL * CL; if (grid_d > n_sm) grid_d = n_sm / CL * CL;
-  if (CL == 4) e = launch_clustered(tc_dgrad<true, 4>, grid_d, 320, DG_TOTAL, 4, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
-  else if (CL == 2) e = launch_clustered(tc_dgrad<true, 2>, grid_d, 320, DG_TOTAL, 2, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
-  else e = launch_clustered(tc_dgrad<true, 1>, grid_d, 320, DG_TOTAL, 1, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, write_dy);
+  auto launch_dgrad = [&](int wr) {
+    if (CL == 4) return launch_clustered(tc_dgrad<true, 4>, grid_d, 320, DG_TOTAL, 4, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, wr);
+    if (CL == 2) return launch_clustered(tc_dgrad<true, 2>, grid_d, 320, DG_TOTAL, 2, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, wr);
+    return launch_clustered(tc_dgrad<true, 1>, grid_d, 320, DG_TOTAL, 1, st, a, (const unsigned char*)img_t, P, L.M, n_tiles, wr);
+  };
+  if (wg16) {
+    if (wg_seed) {   // no history yet: one pass of the chain that only measures max |dY_l| (no planes, no bias gradients)
+      e = cudaMemsetAsync(wg_state, 0, 32 * sizeof(float), st);
+      if (e == cudaSuccess) e = launch_dgrad(0);
+      if (e != cudaSuccess) return e;
+    }
+    wg_scale_update_k<<<1, 32, 0, st>>>(wg_state);
+  }
+  e = launch_dgrad(write_dy);
   if (e != cudaSuccess) return e;
   nnb_prof_mark(st);
   }
@@ -828,13 +1050,14 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
   if (b.g_weights) {
     WgJobs J{};
     int nj = 0;
+    const int pdiv = wg16 ? 2 : 1;     // NNB_WG16: one fp16 plane per tile instead of bf16 hi|lo
     auto add = [&](int dyi, int dy_feat, int xi, int N, int w_off, int ldw, int kvalid, int paired, int cost) {
       WgJob& j = J.j[nj++];
       j.dy = reinterpret_cast<const unsigned char*>(base + L.dyp[dyi]);
-      j.dy_tile = dy_feat == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_128; j.dy_feat = dy_feat;
+      j.dy_tile = (dy_feat == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_128) / pdiv; j.dy_feat = dy_feat;
       j.x = reinterpret_cast<const unsigned char*>(base + L.xp[xi]);
-      j.x_tile = N == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_64;
-      j.N = N; j.ldw = ldw; j.kvalid = kvalid; j.w_off = w_off; j.paired = paired; j.cost = cost;
+      j.x_tile = (N == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_64) / pdiv;
+      j.N = N; j.ldw = ldw; j.kvalid = kvalid; j.w_off = w_off; j.paired = paired; j.cost = wg16 ? (N == 256 ? 48 : 24) * (paired ? 2 : 1) / 2 : cost; j.dyi = dyi;
     };
     // cost = measured MMA-thread cycles per tile and CTA pair (N = 256 tiles are DRAM-bound, N = 64 tiles issue-bound), /80
     add(0, 256, 0, 64, nnb::w_off(0), 63, 63, 1, 40);                                        // layer 0: X = enc (biases: tc_dgrad / ray_dir_grad)
@@ -845,7 +1068,9 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
     J.njobs = nj; J.n_tiles = n_tiles;
     { static const int xlo = [] { const char* v = getenv("NNB_DBG_FWD"); return (v && (atoi(v) & 4)) ? 0 : 1; }(); J.x_lo = xlo; }
     const int grid_w = n_sm >= 2 ? (n_sm / 2) * 2 : 2;
-    tc_wgrad<true><<<grid_w, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);
+    J.wg_state = wg_state;
+    if (wg16) tc_wgrad16<<<grid_w, 192, W16_TOTAL, st>>>(J, b.g_weights);
+    else tc_wgrad<true><<<grid_w, 192, WG_TOTAL, st>>>(J, b.g_weights, gmax);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     {  // small heads: fc_density / fc_rgb (streaming reduction); the direction slice of rgb_layers.0 rides on ray_dir_grad

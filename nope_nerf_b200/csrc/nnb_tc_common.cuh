@@ -93,8 +93,11 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
 //   v  = relu ? max(-nx, 0) : -nx (negation is a free operand modifier)
 //   gate bit = sign(nx)           (x > 0  <=>  nx < 0), shifted into `mw` MSB-first: column j ends up at bit 31 - j
 //   fp16 hi | lo split of v       (x = hi + lo to ~2^-22), written as the next layer's A operand (8 x 16 B per half)
+//   hw[16] (optional)         : the 16 packed fp16 hi words of the chunk (column pairs in order) -- with NNB_WG16 they ARE the X
+//                                operand plane of the weight-gradient pass, no second conversion
 template <bool RELU>
-__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* nbias, float* v, unsigned char* hi_dst, unsigned char* lo_dst, bool write_a) {
+__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* nbias, float* v, unsigned char* hi_dst, unsigned char* lo_dst, bool write_a,
+                                                uint32_t* hw = nullptr) {
   uint32_t mw = 0;
   const ulonglong2* nb = reinterpret_cast<const ulonglong2*>(nbias);
 #pragma unroll
@@ -124,9 +127,18 @@ __device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* 
     if (write_a) {
       *reinterpret_cast<uint4*>(hi_dst + kb * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(lo_dst + kb * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (hw) { hw[kb * 4] = hi[0]; hw[kb * 4 + 1] = hi[1]; hw[kb * 4 + 2] = hi[2]; hw[kb * 4 + 3] = hi[3]; }
     }
   }
   return mw;
+}
+// fp16 (saturating) of 8 values times a power-of-two scale, streamed to global memory: one plane of a NNB_WG16 dY operand
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t d; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d;
+}
+__device__ __forceinline__ void stream8_f16_scaled(const float* v, float scale, unsigned char* dst) {
+  st_stream16(dst, make_uint4(pack_half2_sat(v[0] * scale, v[1] * scale), pack_half2_sat(v[2] * scale, v[3] * scale),
+                              pack_half2_sat(v[4] * scale, v[5] * scale), pack_half2_sat(v[6] * scale, v[7] * scale)));
 }
 // bf16 hi (and optionally lo) operand plane of 8 values, streamed to global memory
 __device__ __forceinline__ void plane_stream8_bf16(const float* v, unsigned char* hi_dst, unsigned char* lo_dst, bool with_lo) {
@@ -164,6 +176,23 @@ __device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_d
   }
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// same, and hands back the four packed hi words (NNB_WG16: the encoding's X plane is the hi half of the E operand)
+__device__ __forceinline__ uint4 split_store8_hi(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    float2 hf = __half22float2(hh);
+    __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    hi[i] = *reinterpret_cast<uint32_t*>(&hh);
+    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(hi_dst) = H;
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  return H;
 }
 
 // bf16 hi/lo split (x = hi + lo to ~2^-17, full fp32 exponent range): used for GRADIENT operands, whose

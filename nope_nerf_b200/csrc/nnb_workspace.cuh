@@ -20,6 +20,7 @@ struct WsLayout {
   size_t dyp[10];   // dY planes: 0..7 = dy0..dy7, 8 = dfeat, 9 = dyr (128 feat)
   size_t mask;      // uint32 [9 layers][Mpad][8]: ReLU sign bits of h0..h7 and (slot 8, 4 words) of the rgb hidden layer
   size_t gmax;      // uint32 bits of max |g| (gradient scaling)
+  size_t wgstate;   // NNB_WG16 scratch state (32 floats) for calls without a caller-owned wg_state
   size_t total;  // bytes
 };
 constexpr size_t PLANE_TILE_256 = 131072, PLANE_TILE_128 = 65536, PLANE_TILE_64 = 32768;
@@ -49,6 +50,7 @@ inline WsLayout make_layout(int N, int S, uint32_t flags, int engine) {
       L.dyp[9] = take(L.n_tiles * PLANE_TILE_128);
       L.mask = take(L.Mpad * 9 * 8 * 4);
       L.gmax = take(256);
+      L.wgstate = take(256);
     } else {  // fp32 [sample][feature] stash (SIMT backward; also consumed after a TC forward)
       for (int l = 0; l < 8; ++l) L.h[l] = take(L.Mpad * 256 * 4);
       L.feat = take(L.Mpad * 256 * 4); L.hr = take(L.Mpad * 128 * 4);

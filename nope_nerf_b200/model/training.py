@@ -40,6 +40,7 @@ class _FlatAdam:
         self.ok = self._supported()
         self.nsteps = 0              # steps taken so far (source of truth shared with the CUDA-graph path)
         self._synced = True
+        self._ready = False          # moment buffers adopted into optimizer.state (re-checked after load_state_dict)
         self._loaded = False         # optimizer.load_state_dict() happened since the last step: adopt ITS step count
         try:
             optimizer.register_state_dict_pre_hook(lambda opt: self.sync_step_tensors())
@@ -52,6 +53,7 @@ class _FlatAdam:
 
     def _mark_loaded(self):
         self._loaded = True
+        self._ready = False
 
     def adopt_loaded_step(self):
         """torch.optim.Adam continues bias correction from the loaded 'step' (checkpoint resume, train.py:60-67); so do we"""
@@ -72,6 +74,9 @@ class _FlatAdam:
 
     def ensure_state(self):
         """allocate / adopt the moment buffers without stepping"""
+        if self._ready and not self._loaded:
+            return                   # per-step fast path: nothing changed since the last adoption
+        self._ready = True
         g = self.opt.param_groups[0]
         if self.flat_param is not None:
             flat = self.flat_param(); plist = list(g['params']); n = flat.numel()
@@ -276,17 +281,18 @@ class _GraphStep:
         ws = call.ws
         call.pooled = False                                 # memory referenced by a captured graph never returns to the pool
         bw = (self.g_rgb, self.g_dp, None if tr.detach_gt_depth else self.g_dg, gbuf[:L.NUM_PARAMS], g_c2w, None, None, g_ss)
+        wgk = tr._wg_kwargs()
         if not self.use_ref:
-            call.backward(*bw)
+            call.backward(*bw, **wgk)
         else:
             # The reference-image stage only needs the two poses / distortions / frames.  It is forked beside the weight-gradient
             # kernel of the render backward: tc_wgrad sits on the HBM roofline with the SIMT pipes idle (192 threads, 108 registers per
             # SM), so the brute-force chamfer's blocks run in its shadow; its pose / distortion gradients accumulate (atomics) into the
             # buffers the render backward also accumulates into.
-            call.backward(*bw, phase=1)
+            call.backward(*bw, phase=1, **wgk)
             cur = torch.cuda.current_stream()
             self.side.wait_stream(cur)
-            call.backward(*bw, phase=2)
+            call.backward(*bw, phase=2, **wgk)
             with torch.cuda.stream(self.side):
                 ops.pose_fwd_dev(pose.r.detach(), pose.t.detach(), init, self.idx_ref, self.c2w_ref)
                 ops.distortion_fwd_dev(dnet.global_scales.detach(), dnet.global_shifts.detach(), self.idx_ref, dnet.fix_scaleN, self.ss_ref)
@@ -360,12 +366,16 @@ class _GraphStep:
             self.meta_last = meta
         self.dev_refs = keep
         cm = data.get('img.camera_mat')
-        if self.cam_host is None or (cm.device.type == 'cpu' and not torch.equal(cm.reshape(4, 4), self.cam_host)):
+        cm_key = (cm.data_ptr(), cm._version)
+        if cm.device.type == 'cpu' and self.cam_host is not None and getattr(self, 'cam_key', None) == cm_key:
+            pass                                              # same host tensor as last step, unmodified
+        elif self.cam_host is None or (cm.device.type == 'cpu' and not torch.equal(cm.reshape(4, 4), self.cam_host)):
             _host_diag_check(cm)
             self.cam_host = cm.reshape(4, 4).clone() if cm.device.type == 'cpu' else None
             self.cam.copy_(cm.reshape(4, 4))
         elif cm.device.type != 'cpu':
             self.cam.copy_(cm.reshape(4, 4))
+        self.cam_key = cm_key
         if self.wts_host != wts:
             self.wts.copy_(torch.tensor(wts, dtype=torch.float32)); self.wts_host = list(wts)
         fas = self._adams()
@@ -414,10 +424,13 @@ class _GraphStep:
         # per-call snapshot (ONE small kernel): later steps overwrite the persistent buffers the graph writes to, and train.py
         # keeps loss_dict['scale'/'shift'] per view (train.py:215-216)
         snap = torch.cat([(tr._peer.reduced if tr._peer is not None else tr._gbuf)[-4:], self.ss, self.rs_losses])
-        zero = snap.new_zeros(())
-        return {'loss': snap[0], 'loss_rgb': snap[1], 'loss_depth': snap[2], 'l2_mean': snap[3],
-                'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': snap[6] if wts[2] != 0.0 else zero,
-                'loss_rgb_s': snap[7] if wts[3] != 0.0 else zero, 'loss_depth_consistency': zero, 'scale': snap[4:5], 'shift': snap[5:6]}
+        s_ = snap.unbind(0)
+        if getattr(self, 'zero', None) is None:
+            self.zero = snap.new_zeros(())
+        zero = self.zero
+        return {'loss': s_[0], 'loss_rgb': s_[1], 'loss_depth': s_[2], 'l2_mean': s_[3],
+                'loss_dist_1st': zero, 'loss_dist_2nd': zero, 'loss_pc': s_[6] if wts[2] != 0.0 else zero,
+                'loss_rgb_s': s_[7] if wts[3] != 0.0 else zero, 'loss_depth_consistency': zero, 'scale': snap[4:5], 'shift': snap[5:6]}
 
 
 class Trainer(object):
@@ -466,6 +479,7 @@ class Trainer(object):
             raise ValueError("dp_mode='rays': training.n_training_points (%d) must be a multiple of the world size (%d): every rank "
                              "takes ray_idx[rank::world] and the loss normalisation assumes equal shards" % (self.n_training_points, self.world))
         self._gbuf = None
+        self._wg_state = None; self._wg_seeded = False
         self._peer = None
         # data-parallel exchange: ONE kernel over NVLink peer memory (all-reduce fused with the Adam updates, captured in the step
         # graph); peer_exchange=False / NNB_PEER_EXCHANGE=0 falls back to torch.distributed.all_reduce between two graphs
@@ -485,6 +499,16 @@ class Trainer(object):
         self.pixel_sampler = kwargs.get('pixel_sampler', 'auto')
 
     # ------------------------------------------------------------------------------------
+    def _wg_kwargs(self):
+        """persistent dY-scale state of the fp16 weight-gradient planes (NNB_WG16 'delayed scaling'): every step's data-gradient chain
+        records max |dY_l|, the next step scales its fp16 dY planes with it; the very first step measures them in an extra pass"""
+        if self._wg_state is None:
+            self._wg_state = torch.zeros(32, device=self.device)
+            self._wg_seeded = False
+        kw = dict(wg_state=self._wg_state, wg_seed=not self._wg_seeded)
+        self._wg_seeded = True
+        return kw
+
     def _grad_buffer(self, peer_step=False):
         """[MLP 595844 | r 3V | t 3V | scales V | shifts V | loss scalars 4], zeroed; the kernels accumulate into it.
         Installed as every parameter's .grad -- except in a peer-exchange step (data parallel, nnb_allreduce_adam), where .grad
@@ -749,7 +773,7 @@ class Trainer(object):
                 g_c2w = torch.zeros(4, 4, device=device)
                 g_ss = torch.zeros(2, device=device)
                 g_cam = torch.zeros(4, 4, device=device) if fxfy is not None else None
-                call.backward(g_rgb, g_dp, None if self.detach_gt_depth else g_dg, gbuf[:L.NUM_PARAMS], g_c2w, g_cam, None, g_ss)
+                call.backward(g_rgb, g_dp, None if self.detach_gt_depth else g_dg, gbuf[:L.NUM_PARAMS], g_c2w, g_cam, None, g_ss, **self._wg_kwargs())
                 ops.pose_bwd_raw(pose.r.detach(), pose.t.detach(), init, img_idx, g_c2w,
                                  gv['r'] if pose.r.requires_grad else None, gv['t'] if pose.t.requires_grad else None)
                 # chain d/d(scale_eff, shift) into global_scales / global_shifts (clamp / fixed-last-view aware)

@@ -201,10 +201,18 @@ def _build_trainer(g, engine_name, with_ref):
 
 @pytest.mark.parametrize("name,with_ref", [("train_render_only", False), ("train_full_losses", True), ("train_full_lastview", True),
                                            ("train_learn_focal", True)])
-@pytest.mark.parametrize("eng", ["simt", "tc"])
-def test_trainer_step_vs_reference_golden(name, with_ref, eng, monkeypatch):
+@pytest.mark.parametrize("eng,wg", [("simt", "exact"), ("tc", "exact"), ("tc", "fp16")])
+def test_trainer_step_vs_reference_golden(name, with_ref, eng, wg, monkeypatch):
+    """Two consecutive reference Trainer.train_step calls.  wg = weight-gradient operand planes of the tcgen05 backward: 'exact' (bf16
+    hi|lo, three MMAs per product) or 'fp16' (NNB_WG16, the default: one fp16 plane per operand, delayed per-layer dY scaling).  With
+    'fp16' the FIRST step's MLP gradients carry fp16 operand rounding (gate 2e-3 on the digests, measured 1.3e-4 .. 2e-4 here and
+    3e-4 rel-L2 per tensor at 1024 x 128, tools/wg16_check.py); Adam's sign-like first update turns that into lr-sized differences on
+    weights whose gradient is near zero, so the SECOND step's gradients agree to 5e-2 only (measured 1.8e-2); pose / distortion
+    gradients of the first step and every loss scalar keep the 'exact' gates."""
     if dict(engines()).get(eng) is None:
         pytest.skip("engine disabled")
+    from nope_nerf_b200 import ops as _ops
+    monkeypatch.setattr(_ops, "_WGRAD", [wg])
     g = load_golden(name)
     trainer, net, pose, dist = _build_trainer(g, eng, with_ref)
     kx, ky = float(g["kx"]), float(g["ky"])
@@ -242,10 +250,14 @@ def test_trainer_step_vs_reference_golden(name, with_ref, eng, monkeypatch):
     if "focal0" in g:
         fo = trainer._test_focal
         worst["focal_end"] = relmax(np.array([fo.fx.item(), fo.fy.item()]) - g["focal0"], g["focal_end"] - g["focal0"])
-    _report("%s/%s" % (name, eng), **worst)
+    _report("%s/%s%s" % (name, eng, "" if wg == "exact" else "-wg16"), **worst)
     for k, v in worst.items():
         if k.startswith("loss"):
             assert v < 2e-4, (k, v)        # loss scalars (L1 sums of N*3 terms, fp32)
+        elif wg == "fp16" and k.startswith("g_") and not k.endswith("_0"):
+            assert v < 5e-2, (k, v)        # second step after an Adam update of fp16-rounded weight gradients (docstring)
+        elif wg == "fp16" and k == "g_params_0":
+            assert v < 2e-3, (k, v)
         elif k.startswith("g_params"):
             assert v < 5e-3, (k, v)        # digests of 24 tensors incl. near-zero ones; second step: parameters already differ by Adam noise
         elif k.startswith("g_"):
@@ -253,7 +265,7 @@ def test_trainer_step_vs_reference_golden(name, with_ref, eng, monkeypatch):
         elif k in ("r_end", "t_end", "focal_end"):
             assert v < 5e-2, (k, v)        # Adam's first steps are ~ lr * sign(g): tiny gradients flip easily
         else:
-            assert v < 1e-3, (k, v)
+            assert v < (5e-3 if wg == "fp16" else 1e-3), (k, v)       # params_end digest (fp16: measured 1.3e-3)
 
 
 @pytest.mark.parametrize("name", ["render_tanks_noise", "render_ndc_distalpha"])
@@ -469,15 +481,21 @@ def test_graph_replay_equals_eager_on_injected_draws(full, monkeypatch):
     le, lg = res[False][0], res[True][0]
     w0 = O.flatten_params(O.init_params(seed=9, hf_damp=True)).astype(np.float64)
     ug, ue = res[True][1] - w0, res[False][1] - w0                        # the 8 Adam updates of every MLP weight
+    r0 = (torch.randn(V, 3, generator=torch.Generator().manual_seed(5)) * 0.03).numpy().astype(np.float64)
+    t0 = (torch.randn(V, 3, generator=torch.Generator().manual_seed(6)) * 0.03).numpy().astype(np.float64)
+    upd = lambda k, p0: np.linalg.norm((res[True][k] - p0) - (res[False][k] - p0)) / max(np.linalg.norm(res[False][k] - p0), 1e-30)
     e = dict(loss=np.abs(le - lg).max() / np.abs(le).max(), w=np.linalg.norm(ug - ue) / np.linalg.norm(ue), w_max=relmax(ug, ue),
-             r=relmax(res[True][2], res[False][2]), t=relmax(res[True][3], res[False][3]), shifts=relmax(res[True][4], res[False][4]))
+             r=upd(2, r0), t=upd(3, t0), r_abs=np.abs(res[True][2] - res[False][2]).max(), t_abs=np.abs(res[True][3] - res[False][3]).max(),
+             shifts=relmax(res[True][4], res[False][4]))
     _report("graph_vs_eager/%s" % ("full" if full else "render"), **e)
     if full:
         assert le[:, 3].min() > 0 and le[:, 4].min() > 0, le             # the reference-image terms were live
     assert e["loss"] < 1e-5, (e, le, lg)
     # Adam turns a gradient into ~lr * sign(g) while |g| is tiny: weights whose gradient sits at the noise of the fp32 atomics can end up
-    # a few lr apart (w_max), the update as a whole agrees (L2)
-    assert e["w"] < 2e-2 and e["r"] < 1e-3 and e["t"] < 1e-3 and e["shifts"] < 1e-3, e
+    # a few lr apart (w_max), the update as a whole agrees (L2).  Pose: same metric on the 8 accumulated updates (a component whose
+    # gradient cancels to the atomics' noise may differ by a fraction of one lr = 5e-4 step: measured 1.8e-4 on one t component, i.e.
+    # 2 % of the L2 norm of the 18 accumulated t updates; the MLP statistic averages over 6e5 weights and is stable at 5.6e-3)
+    assert e["w"] < 2e-2 and e["r"] < 0.1 and e["t"] < 0.1 and e["r_abs"] < 5e-4 and e["t_abs"] < 5e-4 and e["shifts"] < 1e-3, e
 
 
 def test_adam_resume_from_checkpoint_matches_torch():
