@@ -13,13 +13,17 @@
 //                 K-major core-matrix layout); then, from the same registers, density / colour heads and
 //                 the training stash (bf16 operand planes, ReLU bitmasks, fp32 side stash).
 //
-// Two 256-column TMEM accumulators alternate between consecutive layers and the A operand becomes
-// ready in 64-column blocks (one mbarrier each), so layer l+1's MMAs start while layer l's epilogue
-// is still converting: per layer the critical path is max(MMA, epilogue), not their sum.
+// N-half pipeline: every 256-wide GEMM runs as two 128-column halves with one 128-column TMEM accumulator each, and the A operand
+// ALTERNATES between shared memory (odd layers, tcgen05.mma "ss" form) and tensor memory (even layers, "ts" form: lane = sample row,
+// two k per 32-bit column).  The epilogue of layer g therefore writes the next A operand into the medium the running MMAs of layer
+// g do NOT read: it converts half 0 (A blocks 0,1 of layer g+1) while the tensor core is still busy with half 1, and layer g+1
+// starts its first K-steps the moment half 1 is issued -- per layer the tensor pipe only waits for the epilogue of the LAST half
+// (blocks 2,3) instead of for the first chunk of a 256-column accumulator plus the pacing of all four blocks.
 //
 // Shared memory operand layout (no swizzle, "interleaved"): element (row, k) of a [rows x K] fp16
 // operand lives at byte  (k/8) * rows*16 + row*16 + (k%8)*2 : 8x8 core matrices of 128 contiguous
 // bytes, SBO = 128 B between row-groups, LBO = rows*16 B between the two k-halves of one MMA.
+// Tensor memory map (512 columns): [0,256) the two half accumulators, [256,384) A hi, [384,512) A lo (even layers).
 #include "nnb_tc_common.cuh"
 #include <cstdlib>
 
@@ -32,13 +36,13 @@ namespace {
 
 constexpr int TILE = 128;
 constexpr int NST = 3;                      // weight ring depth
-constexpr int STAGE_BYTES = 16384;          // 256 rows x 16 k x (hi + lo) fp16
+constexpr int STAGE_BYTES = 16384;          // 128 rows x 32 k x (hi + lo) fp16 = two K-steps of one 128-column half
 constexpr int N_GEMM = 10;                  // L0..L7, feature, rgb-hidden
-// ---- stage table: the order in which weight k-slices are consumed for one tile -----------------
-struct StageDesc { int w_off, ldw, kcol0, kvalid, nrows, img_off; };
-constexpr int N_STAGES = 4 + 3 * 16 + (4 + 16) + 3 * 16 + 16 + 16;   // 152
+// ---- stage table: the order in which weight stages are consumed for one tile: layer, half, k-group -----------------
+struct StageDesc { int w_off, ldw, kcol0, kvalid, row0, img_off; };
+constexpr int N_STAGES = 2 * 2 + 3 * 16 + 2 * (2 + 8) + 3 * 16 + 16 + 8;   // 144
 __constant__ StageDesc c_stages[N_STAGES];
-constexpr size_t IMG_BYTES = (size_t)(N_STAGES - 16) * STAGE_BYTES + 16 * (STAGE_BYTES / 2);
+constexpr size_t IMG_BYTES = (size_t)N_STAGES * STAGE_BYTES;
 
 // shared memory map (bytes)
 constexpr int SM_AHI = 0, SM_ALO = 65536, SM_EHI = 131072, SM_ELO = 147456, SM_W = 163840;
@@ -50,6 +54,7 @@ constexpr int SM_BAR = SM_PART + 128 * 4 * 4;                // head partial sum
 constexpr int SM_TOTAL = SM_BAR + 32 * 8 + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 enum { B_FULL = 0, B_EMPTY = NST, B_AREADY = 2 * NST, B_EREADY = 2 * NST + 4, B_ACCFULL = 2 * NST + 5, B_ACCEMPTY = 2 * NST + 7, B_COUNT = 2 * NST + 9 };
+constexpr uint32_t TM_AHI = 256, TM_ALO = 384;   // tensor-memory columns of the even layers' A operand
 
 using namespace tcu;
 
@@ -57,17 +62,17 @@ using namespace tcu;
 __global__ void tc_prep_weights(const float* __restrict__ w, unsigned char* __restrict__ img) {
   const int s = blockIdx.x;
   const StageDesc sd = c_stages[s];
-  unsigned char* hi = img + sd.img_off;
-  unsigned char* lo = hi + sd.nrows * 32;
-  for (int idx = threadIdx.x; idx < sd.nrows * 2; idx += blockDim.x) {
-    int n = idx % sd.nrows, ko = idx / sd.nrows;   // k-octet 0/1
+  unsigned char* hi = img + sd.img_off;       // [k-octet 0..3][128 rows][8] fp16
+  unsigned char* lo = hi + 8192;
+  for (int idx = threadIdx.x; idx < 128 * 4; idx += blockDim.x) {
+    const int n = idx & 127, ko = idx >> 7;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int k = sd.kcol0 + ko * 8 + j;
-      v[j] = (k < sd.kvalid) ? __ldg(w + sd.w_off + (size_t)n * sd.ldw + k) : 0.f;
+      const int k = sd.kcol0 + ko * 8 + j;
+      v[j] = (k < sd.kvalid) ? __ldg(w + sd.w_off + (size_t)(sd.row0 + n) * sd.ldw + k) : 0.f;
     }
-    split_store8(v, hi + ko * sd.nrows * 16 + n * 16, lo + ko * sd.nrows * 16 + n * 16);
+    split_store8(v, hi + ko * 2048 + n * 16, lo + ko * 2048 + n * 16);
   }
 }
 
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: all 512 columns (two 256-column fp32 accumulators)
+  if (warp == 1) {  // TMEM: all 512 columns (two 128-column half accumulators + the even layers' A operand hi | lo)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
       uint32_t slot = 0, phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
         for (int s = 0; s < N_STAGES; ++s) {
-          const int bytes = c_stages[s].nrows * 64;
+          const int bytes = STAGE_BYTES;
           mbar_wait(BAR(B_EMPTY + slot), phase ^ 1);          // all CL consumers released this slot
           mbar_expect_tx(BAR(B_FULL + slot), bytes);
           if (CL == 1) bulk_g2s(smem_u32(smem + SM_W + slot * STAGE_BYTES), wimg + c_stages[s].img_off, bytes, BAR(B_FULL + slot));
@@ -182,51 +187,60 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           }
           continue;
         }
+        const uint32_t idesc = make_idesc(128, 128);
         for (int g = 0; g < N_GEMM; ++g) {
-          const int buf = g & 1;
-          const uint32_t use = (uint32_t)tv * 5u + (uint32_t)(g >> 1);
-          PROF_T0();
-          mbar_wait(BAR(B_ACCEMPTY + buf), (use & 1u) ^ 1u);
-          tc_fence_after();
-          PROF_ADD(0);
-          const uint32_t d_tmem = tmem_base + buf * 256;
-          const int N = (g == 9) ? 128 : 256;
-          const uint32_t idesc = make_idesc(128, N);
-          const uint32_t b_lbo = N * 16;
-          const int e_steps = (g == 0 || g == 4) ? 4 : 0;
-          const int a_steps = (g == 0) ? 0 : 16;
-          if (e_steps) { if (g == 0) { mbar_wait(BAR(B_EREADY), (uint32_t)tv & 1u); tc_fence_after(); } }
-          PROF_ADD(1);
-          uint32_t acc = 0;
-          uint32_t full_ok = mbar_probe(BAR(B_FULL + slot), phase);    // probe early: its latency hides under the other waits
-          for (int ks = 0; ks < e_steps + a_steps; ++ks) {
-            uint32_t ahi, alo;
-            if (ks < e_steps) { ahi = e_hi + ks * 4096; alo = e_lo + ks * 4096; }
-            else {
-              const int ka = ks - e_steps;
-              if ((ka & 3) == 0) {  // first k-step of a 64-column block: wait for the previous epilogue
-                const uint32_t au = (uint32_t)tv * 9u + (uint32_t)(g - 1);
-                mbar_wait(BAR(B_AREADY + (ka >> 2)), au & 1u);
-                tc_fence_after();
-              }
-              ahi = a_hi + ka * 4096; alo = a_lo + ka * 4096;
-            }
-            PROF_ADD(2);
-            if (!full_ok) mbar_wait(BAR(B_FULL + slot), phase);
+          const int e_ksteps = (g == 0 || g == 4) ? 4 : 0;        // K-steps fed by the encoding operand E (shared memory)
+          const int a_ksteps = (g == 0) ? 0 : 16;                 // K-steps fed by the previous layer's output
+          const bool a_tmem = (g & 1) == 0;                       // even layers read A from tensor memory (written by the odd layer before)
+          const int nhalf = (g == 9) ? 1 : 2;
+          for (int h = 0; h < nhalf; ++h) {
+            const uint32_t use = h ? (uint32_t)tv * 9u + (uint32_t)g : (uint32_t)tv * 10u + (uint32_t)g;
+            PROF_T0();
+            mbar_wait(BAR(B_ACCEMPTY + h), (use & 1u) ^ 1u);      // the epilogue of the previous layer has drained this half accumulator
             tc_fence_after();
-            PROF_ADD(3);
-            const uint32_t wb = smem_u32(smem + SM_W + slot * STAGE_BYTES);
-            const uint64_t dAh = make_desc(ahi, 2048, 128), dAl = make_desc(alo, 2048, 128);
-            const uint64_t dBh = make_desc(wb, b_lbo, 128), dBl = make_desc(wb + N * 32, b_lbo, 128);
-            {   // the NEXT stage's barrier is probed inside the same instruction group: its round trip overlaps the MMA issue / commit
+            PROF_ADD(0);
+            const uint32_t d_tmem = tmem_base + h * 128;
+            if (g == 0 && h == 0) { mbar_wait(BAR(B_EREADY), (uint32_t)tv & 1u); tc_fence_after(); }
+            PROF_ADD(1);
+            uint32_t acc = 0;
+            uint32_t full_ok = mbar_probe(BAR(B_FULL + slot), phase);    // probe early: its latency hides under the other waits
+            for (int ks = 0; ks < e_ksteps + a_ksteps; ks += 2) {       // one 16 KB weight stage = two K-steps
+              uint64_t aL0, aH0, aL1, aH1;
+              bool ts = false;
+              if (ks < e_ksteps) {
+                aH0 = make_desc(e_hi + ks * 4096, 2048, 128); aL0 = make_desc(e_lo + ks * 4096, 2048, 128);
+                aH1 = make_desc(e_hi + (ks + 1) * 4096, 2048, 128); aL1 = make_desc(e_lo + (ks + 1) * 4096, 2048, 128);
+              } else {
+                const int ka = ks - e_ksteps;
+                if ((ka & 3) == 0 && h == 0) {  // first K-step of a 64-column block of A: wait for the previous layer's epilogue (half 1 re-reads)
+                  const uint32_t au = (uint32_t)tv * 9u + (uint32_t)(g - 1);
+                  mbar_wait(BAR(B_AREADY + (ka >> 2)), au & 1u);
+                  tc_fence_after();
+                }
+                if (a_tmem) {
+                  ts = true;
+                  aH0 = tmem_base + TM_AHI + ka * 8; aL0 = tmem_base + TM_ALO + ka * 8; aH1 = aH0 + 8; aL1 = aL0 + 8;
+                } else {
+                  aH0 = make_desc(a_hi + ka * 4096, 2048, 128); aL0 = make_desc(a_lo + ka * 4096, 2048, 128);
+                  aH1 = make_desc(a_hi + (ka + 1) * 4096, 2048, 128); aL1 = make_desc(a_lo + (ka + 1) * 4096, 2048, 128);
+                }
+              }
+              PROF_ADD(2);
+              if (!full_ok) mbar_wait(BAR(B_FULL + slot), phase);
+              tc_fence_after();
+              PROF_ADD(3);
+              const uint32_t wb = smem_u32(smem + SM_W + slot * STAGE_BYTES);   // [hi: k-octet 0..3][128][8] | [lo: ...], 4096 B per K-step
+              const uint64_t bH0 = make_desc(wb, 2048, 128), bL0 = make_desc(wb + 8192, 2048, 128);
+              const uint64_t bH1 = make_desc(wb + 4096, 2048, 128), bL1 = make_desc(wb + 8192 + 4096, 2048, 128);
               const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
-              full_ok = tc_stage_mma3<CL>(d_tmem, dAl, dAh, dBh, dBl, idesc, acc, BAR(B_EMPTY + slot), cmask, BAR(B_FULL + nslot), nphase);
+              if (ts) full_ok = tc_stage_mma6<CL, true>(d_tmem, aL0, aH0, aL1, aH1, bH0, bL0, bH1, bL1, idesc, acc, BAR(B_EMPTY + slot), cmask, BAR(B_FULL + nslot), nphase);
+              else full_ok = tc_stage_mma6<CL, false>(d_tmem, aL0, aH0, aL1, aH1, bH0, bL0, bH1, bL1, idesc, acc, BAR(B_EMPTY + slot), cmask, BAR(B_FULL + nslot), nphase);
+              acc = 1u;
+              if (++slot == NST) { slot = 0; phase ^= 1; }
+              PROF_ADD(4);
             }
-            acc = 1u;
-            if (++slot == NST) { slot = 0; phase ^= 1; }
-            PROF_ADD(4);
+            tc_commit(BAR(B_ACCFULL + h));
           }
-          tc_commit(BAR(B_ACCFULL + buf));
         }
         ++tv;
       }
@@ -339,25 +353,20 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
       PROF_ADD(0);
       // ---- per-GEMM epilogues ----
       for (int g = 0; g < N_GEMM; ++g) {
-        const int buf = g & 1;
-        const uint32_t use = (uint32_t)t * 5u + (uint32_t)(g >> 1);
-        mbar_wait(BAR(B_ACCFULL + buf), use & 1u);
-        tc_fence_after();
-        PROF_ADD(1);
-        const int nch = (g == 9) ? 2 : 4;                 // chunks of 32 columns handled by this half
         const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
         const bool planes = stash && (st.tcb & 1);
         const int dbg = st.tcb >> 1;
         const bool wg16 = st.wg16 != 0;
         unsigned char* xplane = (planes && g < 9 && !(dbg & 1)) ? st.xp[1 + g] + (size_t)tile * (wg16 ? PLANE_TILE_256 / 2 : PLANE_TILE_256) + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
-        // Per 32-column chunk: (1) critical path of the MMA warp: accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand,
-        // block by block (the two halves convert adjacent chunks of the SAME 64-column block, so block `ci` is complete
-        // after one chunk time); (2) after the block is signalled, from the same registers, everything the next MMA does
-        // not need: density / colour heads, fp32 side stash, bf16 operand planes, ReLU bitmasks.  One chunk takes less
-        // than the 4 K-steps (~1.5k cycles) the tensor core spends on a block, so (2) never starves the MMA warp.
-        const bool two_pass = false;
+        // Per 32-column chunk: (1) critical path of the MMA warp: accumulator -> bias/ReLU -> fp16 hi|lo -> next A operand (shared
+        // memory for an odd next layer, tensor memory for an even one), block by block: the two thread halves convert adjacent
+        // chunks of the SAME 64-column block, so a block is complete after one chunk time; (2) after the block is signalled, from the
+        // same registers, everything the next MMA does not need: density / colour heads, fp32 side stash, operand planes, ReLU
+        // bitmasks.  The A operand of layer g+1 lives in the medium layer g's MMAs do not read, so half 0 is converted while the
+        // tensor core still works on half 1.
         const bool need2 = (g == 7) || (g == 9) || stash;
         const bool x_lo = !(dbg & 4);            // X planes carry the bf16 lo half too (NNB_DBG_FWD bit 2: hi only, experiment)
+        const bool next_tmem = (g & 1) == 1;     // layer g+1 is even -> its A operand goes to tensor memory
         auto side_work = [&](int cb, const float* v, uint32_t mw, const uint32_t* hw) {
           if (g == 7) {
 #pragma unroll
@@ -389,28 +398,42 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           if (planes && (g < 8 || g == 9) && !(dbg & 2))     // ReLU gate bits of this 32-column chunk (g = 9: rgb hidden layer, slot 8);
             __stcs(st.mask + ((size_t)(g < 8 ? g : 8) * st.Mpad + m) * 8 + cb, mw);   // column j at bit 31 - j (epi_chunk32)
         };
+        const int nhalf = (g == 9) ? 1 : 2;
 #pragma unroll 1
-        for (int ci = 0; ci < nch; ++ci) {
-          const int cb = 2 * ci + half;
-          uint32_t r[32];
-          tc_ld32(lane_addr + buf * 256 + cb * 32, r);
-          PROF_ADD(2);
-          float v[32];
-          uint32_t hw[16];
-          const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, true, hw)
-                                       : epi_chunk32<true>(r, bias + cb * 32, v, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16, g < 9, hw);
-          if (g < 9) {
-            PROF_ADD(3);
-            fence_async_smem();
-            PROF_ADD(4);
-            mbar_arrive(BAR(B_AREADY + ci));     // 256 arrivals (both halves) complete block ci
-            PROF_ADD(5);
+        for (int h = 0; h < nhalf; ++h) {
+          const uint32_t use = h ? (uint32_t)t * 9u + (uint32_t)g : (uint32_t)t * 10u + (uint32_t)g;
+          mbar_wait(BAR(B_ACCFULL + h), use & 1u);
+          tc_fence_after();
+          PROF_ADD(1);
+#pragma unroll 1
+          for (int ci = 0; ci < 2; ++ci) {
+            const int cb = 4 * h + 2 * ci + half;          // 32-column chunk of the layer output; A block of the next layer = cb >> 1
+            uint32_t r[32];
+            tc_ld32(lane_addr + cb * 32, r);
+            PROF_ADD(2);
+            float v[32];
+            uint32_t hw[16], lw[16];
+            const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, hw, lw, true) : epi_chunk32<true>(r, bias + cb * 32, v, hw, lw, g < 9);
+            if (g < 9) {
+              PROF_ADD(3);
+              if (next_tmem) {
+                tc_st16(lane_addr + TM_AHI + cb * 16, hw); tc_st16(lane_addr + TM_ALO + cb * 16, lw);
+                tc_wait_st();
+                tc_fence_before();
+              } else {
+                store_words_smem(hw, lw, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16);
+                fence_async_smem();
+              }
+              PROF_ADD(4);
+              mbar_arrive(BAR(B_AREADY + (cb >> 1)));     // 256 arrivals (both thread halves) complete the block
+              PROF_ADD(5);
+            }
+            if (need2) side_work(cb, v, mw, hw);
           }
-          if (need2 && !two_pass) side_work(cb, v, mw, hw);
+          tc_fence_before();
+          mbar_arrive(BAR(B_ACCEMPTY + h));
+          PROF_ADD(6);
         }
-        tc_fence_before();
-        mbar_arrive(BAR(B_ACCEMPTY + buf));
-        PROF_ADD(6);
       }
       // ---- heads + per-sample record (half 1 hands its partial dot products to half 0) ----
       if (half == 1) {
@@ -448,17 +471,19 @@ cudaError_t upload_stage_table() {
   if (g_stage_table_ready) return cudaSuccess;
   StageDesc h[N_STAGES];
   int s = 0, off = 0;
-  auto add = [&](int w_off, int ldw, int kcol0, int kvalid, int nrows) {
-    h[s].w_off = w_off; h[s].ldw = ldw; h[s].kcol0 = kcol0; h[s].kvalid = kvalid; h[s].nrows = nrows; h[s].img_off = off;
-    off += nrows * 64; ++s;
+  auto add = [&](int w_off, int ldw, int kcol0, int kvalid, int row0) {
+    h[s].w_off = w_off; h[s].ldw = ldw; h[s].kcol0 = kcol0; h[s].kvalid = kvalid; h[s].row0 = row0; h[s].img_off = off;
+    off += STAGE_BYTES; ++s;
   };
-  for (int i = 0; i < 4; ++i) add(nnb::w_off(0), 63, 16 * i, 63, 256);
-  for (int l = 1; l < 8; ++l) {
-    if (l == 4) for (int i = 0; i < 4; ++i) add(nnb::w_off(4), 319, 256 + 16 * i, 319, 256);
-    for (int i = 0; i < 16; ++i) add(nnb::w_off(l), nnb::w_ld(l), 16 * i, 256, 256);
-  }
-  for (int i = 0; i < 16; ++i) add(nnb::W_FEAT, 256, 16 * i, 256, 256);
-  for (int i = 0; i < 16; ++i) add(nnb::W_RGBH, 283, 16 * i, 256, 128);
+  // per layer: half 0 (rows 0..127) then half 1 (rows 128..255); inside a half the encoding K-steps (layers 0 and 4) come first
+  for (int hf = 0; hf < 2; ++hf) for (int i = 0; i < 2; ++i) add(nnb::w_off(0), 63, 32 * i, 63, 128 * hf);
+  for (int l = 1; l < 8; ++l)
+    for (int hf = 0; hf < 2; ++hf) {
+      if (l == 4) for (int i = 0; i < 2; ++i) add(nnb::w_off(4), 319, 256 + 32 * i, 319, 128 * hf);
+      for (int i = 0; i < 8; ++i) add(nnb::w_off(l), nnb::w_ld(l), 32 * i, 256, 128 * hf);
+    }
+  for (int hf = 0; hf < 2; ++hf) for (int i = 0; i < 8; ++i) add(nnb::W_FEAT, 256, 32 * i, 256, 128 * hf);
+  for (int i = 0; i < 8; ++i) add(nnb::W_RGBH, 283, 32 * i, 256, 0);
   if (s != N_STAGES || (size_t)off != IMG_BYTES) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemcpyToSymbol(c_stages, h, sizeof(h));
   if (e == cudaSuccess) g_stage_table_ready = true;
@@ -517,7 +542,7 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
     }
   }
   nnb_prof_mark(st);
-  tc_prep_weights<<<N_STAGES, 256, 0, st>>>(a.weights, img);
+  tc_prep_weights<<<N_STAGES, 256, 0, st>>>(a.weights, img);   // 144 x 16 KB stage images (fp16 hi | lo)
   nnb_prof_mark(st);
   const int n_tiles = (int)((L.M + TILE - 1) / TILE);
   const int CL = cluster_size_option();

@@ -92,46 +92,54 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
 //   nx = (-bias) - acc            (packed; `nbias` holds the NEGATED biases, so nx = -(acc + bias) bit for bit)
 //   v  = relu ? max(-nx, 0) : -nx (negation is a free operand modifier)
 //   gate bit = sign(nx)           (x > 0  <=>  nx < 0), shifted into `mw` MSB-first: column j ends up at bit 31 - j
-//   fp16 hi | lo split of v       (x = hi + lo to ~2^-22), written as the next layer's A operand (8 x 16 B per half)
-//   hw[16] (optional)         : the 16 packed fp16 hi words of the chunk (column pairs in order) -- with NNB_WG16 they ARE the X
-//                                operand plane of the weight-gradient pass, no second conversion
+//   fp16 hi | lo split of v       (x = hi + lo to ~2^-22) as 16 + 16 packed words (column pairs in order, even column in the low
+//                                 half): the next layer's A operand -- the caller stores them to shared memory (core-matrix layout) or
+//                                 to tensor memory (row = lane, two k per column) -- and, with NNB_WG16, hw[] IS the X plane of the
+//                                 weight-gradient pass
 template <bool RELU>
-__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* nbias, float* v, unsigned char* hi_dst, unsigned char* lo_dst, bool write_a,
-                                                uint32_t* hw = nullptr) {
+__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* nbias, float* v, uint32_t* hw, uint32_t* lw, bool want_words) {
   uint32_t mw = 0;
   const ulonglong2* nb = reinterpret_cast<const ulonglong2*>(nbias);
 #pragma unroll
-  for (int kb = 0; kb < 4; ++kb) {
-    uint32_t hi[4], lo[4];
+  for (int q = 0; q < 8; ++q) {          // 4 columns per step
+    const ulonglong2 b4 = nb[q];
 #pragma unroll
-    for (int i = 0; i < 4; i += 2) {
-      const ulonglong2 b4 = nb[kb * 2 + (i >> 1)];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int j = kb * 8 + (i + h) * 2;
-        const unsigned long long nx2 = f2_sub(h ? b4.y : b4.x, u2_pack(r[j], r[j + 1]));
-        float n0, n1; f2_unpack(nx2, n0, n1);
-        if (RELU) {
-          mw = __funnelshift_l(__float_as_uint(n0), mw, 1); mw = __funnelshift_l(__float_as_uint(n1), mw, 1);
-          v[j] = fmaxf(-n0, 0.f); v[j + 1] = fmaxf(-n1, 0.f);
-        } else { v[j] = -n0; v[j + 1] = -n1; }
-        if (write_a) {
-          __half2 hh = __floats2half2_rn(v[j], v[j + 1]);
-          const float2 hf = __half22float2(hh);
-          float l0, l1; f2_unpack(f2_sub(f2_pack(v[j], v[j + 1]), f2_pack(hf.x, hf.y)), l0, l1);
-          __half2 ll = __floats2half2_rn(l0, l1);
-          hi[i + h] = *reinterpret_cast<uint32_t*>(&hh); lo[i + h] = *reinterpret_cast<uint32_t*>(&ll);
-        }
+    for (int h = 0; h < 2; ++h) {
+      const int j = q * 4 + h * 2;
+      const unsigned long long nx2 = f2_sub(h ? b4.y : b4.x, u2_pack(r[j], r[j + 1]));
+      float n0, n1; f2_unpack(nx2, n0, n1);
+      if (RELU) {
+        mw = __funnelshift_l(__float_as_uint(n0), mw, 1); mw = __funnelshift_l(__float_as_uint(n1), mw, 1);
+        v[j] = fmaxf(-n0, 0.f); v[j + 1] = fmaxf(-n1, 0.f);
+      } else { v[j] = -n0; v[j + 1] = -n1; }
+      if (want_words) {
+        __half2 hh = __floats2half2_rn(v[j], v[j + 1]);
+        const float2 hf = __half22float2(hh);
+        float l0, l1; f2_unpack(f2_sub(f2_pack(v[j], v[j + 1]), f2_pack(hf.x, hf.y)), l0, l1);
+        __half2 ll = __floats2half2_rn(l0, l1);
+        hw[j >> 1] = *reinterpret_cast<uint32_t*>(&hh); lw[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
       }
-    }
-    if (write_a) {
-      *reinterpret_cast<uint4*>(hi_dst + kb * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(lo_dst + kb * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      if (hw) { hw[kb * 4] = hi[0]; hw[kb * 4 + 1] = hi[1]; hw[kb * 4 + 2] = hi[2]; hw[kb * 4 + 3] = hi[3]; }
     }
   }
   return mw;
 }
+// the 16 + 16 operand words of a chunk -> shared memory, canonical no-swizzle K-major core matrices (8 x 16 B per half)
+__device__ __forceinline__ void store_words_smem(const uint32_t* hw, const uint32_t* lw, unsigned char* hi_dst, unsigned char* lo_dst) {
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    *reinterpret_cast<uint4*>(hi_dst + kb * 2048) = make_uint4(hw[kb * 4], hw[kb * 4 + 1], hw[kb * 4 + 2], hw[kb * 4 + 3]);
+    *reinterpret_cast<uint4*>(lo_dst + kb * 2048) = make_uint4(lw[kb * 4], lw[kb * 4 + 1], lw[kb * 4 + 2], lw[kb * 4 + 3]);
+  }
+}
+// ... or -> tensor memory (A operand of the .ts MMA form): lane = sample row, column c holds k = 2c, 2c + 1
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // fp16 (saturating) of 8 values times a power-of-two scale, streamed to global memory: one plane of a NNB_WG16 dY operand
 __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
   uint32_t d; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d;
@@ -304,6 +312,58 @@ __device__ __forceinline__ uint32_t tc_stage_mma3(uint32_t d_tmem, uint64_t a_lo
         "selp.u32 %0, 1, 0, q;\n\t}"
         : "=r"(ok)
         : "r"(d_tmem), "l"(a_lo), "l"(a_hi), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask)
+        : "memory");
+  }
+  return ok;
+}
+// One 16 KB weight stage of the N-half pipeline = TWO K-steps of a 128-column half: probe the NEXT stage's "full" barrier, issue the
+// six MMAs (per K-step: a_lo*b_hi [+ restart], a_hi*b_lo, a_hi*b_hi), commit the stage's "empty" barrier, then read the probe.
+// TS = false: A operands are shared-memory descriptors; TS = true: A operands are TENSOR-MEMORY addresses (low 32 bits used).
+template <int CL, bool TS>
+__device__ __forceinline__ uint32_t tc_stage_mma6(uint32_t d_tmem, uint64_t a_lo0, uint64_t a_hi0, uint64_t a_lo1, uint64_t a_hi1, uint64_t b_hi0,
+                                                  uint64_t b_lo0, uint64_t b_hi1, uint64_t b_lo1, uint32_t idesc, uint32_t acc, uint32_t empty_bar,
+                                                  uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
+  uint32_t ok;
+  if (!TS) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%13], %14;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %6, %10, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %7, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %6, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %4, %8, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %9, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %8, %10, t;\n\t"
+        "setp.eq.u32 t, %15, 1;\n\t"
+        "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+        "@!t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], %16;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ok)
+        : "r"(d_tmem), "l"(a_lo0), "l"(a_hi0), "l"(a_lo1), "l"(a_hi1), "l"(b_hi0), "l"(b_lo0), "l"(b_hi1), "l"(b_lo1), "r"(idesc), "r"(acc),
+          "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "r"((uint32_t)CL), "h"(cmask)
+        : "memory");
+  } else {
+    const uint32_t t_lo0 = (uint32_t)a_lo0, t_hi0 = (uint32_t)a_hi0, t_lo1 = (uint32_t)a_lo1, t_hi1 = (uint32_t)a_hi1;
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%13], %14;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %6, %10, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %7, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %6, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%4], %8, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%5], %9, %10, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%5], %8, %10, t;\n\t"
+        "setp.eq.u32 t, %15, 1;\n\t"
+        "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+        "@!t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], %16;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ok)
+        : "r"(d_tmem), "r"(t_lo0), "r"(t_hi0), "r"(t_lo1), "r"(t_hi1), "l"(b_hi0), "l"(b_lo0), "l"(b_hi1), "l"(b_lo1), "r"(idesc), "r"(acc),
+          "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "r"((uint32_t)CL), "h"(cmask)
         : "memory");
   }
   return ok;

@@ -12,4 +12,5 @@ from .eval_pose_one_epoch import Trainer_pose
 from .distortions import Learn_Distortion
 from .losses import Loss, Loss_Eval
 from .extracting_images import Extract_Images
+from .eval_images import Eval_Images
 from . import common

@@ -186,6 +186,7 @@ class _GraphStep:
         self.imgpp = self.meta[2:4]                                       # frame pointers {current, reference}
         self.meta_host = torch.zeros(16, 4, dtype=torch.int64).pin_memory(); self.meta_np = self.meta_host.numpy()
         self.meta_ev = [None] * 16
+        self.ev_pool = []                                   # recycled events of the host-frame keep-alive list
         self.dpt = torch.zeros(hd, wd, device=dev)
         self.cam = torch.zeros(4, 4, device=dev); self.cam_host = None
         self.ss = torch.zeros(2, device=dev)               # effective (scale, shift) of the current view
@@ -348,6 +349,7 @@ class _GraphStep:
 
     def run(self, data, wts):
         tr = self.tr; dev = tr.device
+        cur_stream = torch.cuda.current_stream()
         img, img_keep = self._frame_ptr(data.get('img'), 0)
         meta = [int(data.get('img.idx')), 0, img.data_ptr(), 0]
         keep = [img_keep]
@@ -362,7 +364,8 @@ class _GraphStep:
             if self.meta_ev[k] is not None: self.meta_ev[k].synchronize()   # the slot's previous copy has run (16 steps ago)
             self.meta_np[k] = meta
             self.meta.copy_(self.meta_host[k], non_blocking=True)
-            ev = torch.cuda.Event(); ev.record(); self.meta_ev[k] = ev
+            if self.meta_ev[k] is None: self.meta_ev[k] = torch.cuda.Event()
+            self.meta_ev[k].record(cur_stream)
             self.meta_last = meta
         self.dev_refs = keep
         cm = data.get('img.camera_mat')
@@ -417,10 +420,11 @@ class _GraphStep:
         if any(t.device.type == 'cpu' for t in keep):
             # a page-locked host frame is read IN PLACE (or copied asynchronously) by this step: keep it referenced until the step has
             # run (torch's pinned-memory allocator only tracks torch-issued copies, so a recycled DataLoader buffer could be refilled)
-            ev = torch.cuda.Event(); ev.record()
+            ev = self.ev_pool.pop() if self.ev_pool else torch.cuda.Event()
+            ev.record(cur_stream)
             self.host_refs.append((keep, ev))
             while len(self.host_refs) > 1 and self.host_refs[0][1].query():
-                self.host_refs.pop(0)
+                self.ev_pool.append(self.host_refs.pop(0)[1])
         # per-call snapshot (ONE small kernel): later steps overwrite the persistent buffers the graph writes to, and train.py
         # keeps loss_dict['scale'/'shift'] per view (train.py:215-216)
         snap = torch.cat([(tr._peer.reduced if tr._peer is not None else tr._gbuf)[-4:], self.ss, self.rs_losses])
@@ -551,11 +555,12 @@ class Trainer(object):
 
     def train_step(self, data, it=None, epoch=None, scheduling_start=None, render_path=None):
         """training.py:67-97"""
-        self.model.train()
-        if self.pose_param_net: self.pose_param_net.train()
+        # (nn.Module.train() walks every submodule: ~60 us of host time per step -- only when the mode actually changes)
+        if not self.model.training: self.model.train()
+        if self.pose_param_net and not self.pose_param_net.training: self.pose_param_net.train()
         if self.focal_net:
             self.focal_net.train(); self.optimizer_focal.zero_grad()
-        if self.distortion_net: self.distortion_net.train()
+        if self.distortion_net and not self.distortion_net.training: self.distortion_net.train()
         gs = self._graph_step_or_none(data, epoch, scheduling_start)
         if gs is not None:
             return gs[0].run(data, gs[1])          # fixed kernel sequence; replayed as one CUDA graph when use_cuda_graph

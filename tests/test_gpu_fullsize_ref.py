@@ -204,3 +204,68 @@ def test_render_outputs_vs_live_reference(name):
              depth_gt=rel(outs[1]["depth_gt"], outs[0]["depth_gt"]))
     _report("render/%s" % name, **e)
     assert max(e.values()) < 1e-4, e
+
+
+def _small_scene(H=48, W=64, hd=24, wd=32, V=4, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    up = lambda t, size: torch.nn.functional.interpolate(t, size, mode="bilinear", align_corners=False)
+    fx = 0.6 * W
+    cam = torch.tensor([[2 * fx / W, 0, 0, 0], [0, -2 * fx / H, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], dtype=torch.float32)[None]
+    img = up(torch.rand(1, 3, 6, 8, generator=g), (H, W)).contiguous()
+    dpt = (up(torch.rand(1, 1, 6, 8, generator=g), (hd, wd))[0] * 3.0 + 2.0).contiguous()
+    return {"img": img, "img.idx": torch.tensor([1]), "img.dpt": dpt, "img.camera_mat": cam, "img.scale_mat": torch.eye(4)[None],
+            "img.depth": torch.rand(1, H, W, generator=g) * 5 + 0.5}
+
+
+def test_eval_images_vs_live_reference(tmp_path):
+    """Eval_Images.eval_images (model/eval_images.py:46-137): the reference's chunked Renderer loop + pytorch_ssim against ONE
+    render_frame call + on-device PSNR / SSIM; same learnt poses, same weights"""
+    import nope_nerf_b200.model as mdl
+    from nope_nerf_b200 import ops
+    ops.set_default_engine("tc")
+    H, W, V = 48, 64, 4
+    cfg = RH.load_default_cfg()
+    cfg["extract_images"] = {"resolution": [H, W]}
+    torch.manual_seed(21)
+    rig = RH.RefRig(cfg, V, "cuda")
+    state = _init_state(rig, V, 97)
+    data = _small_scene(H, W, V=V)
+    c2ws = torch.stack([rig.pose(i) for i in range(V)]).detach()
+    import model.eval_images as rei                                   # the REFERENCE's module (oracle/_ref on sys.path)
+    lp = lambda a, b, normalize=True: (a - b).abs().mean()             # stand-in for the LPIPS network (same callable on both sides)
+    ref_ev = rei.Eval_Images(rig.rend, cfg, use_learnt_poses=True, use_learnt_focal=False, device=torch.device("cuda"), render_type="nope_nerf", c2ws=c2ws)
+    d_ref = ref_ev.eval_images(data, str(tmp_path / "ref"), None, lp, None)
+    trainer, net, pose, dist, model = _ours(cfg, V, state)
+    ev = mdl.Eval_Images(model.renderer, cfg, use_learnt_poses=True, use_learnt_focal=False, device=torch.device("cuda"), render_type="nope_nerf", c2ws=c2ws)
+    d = ev.eval_images(data, str(tmp_path / "ours"), None, lp, None)
+    e = dict(mse=abs(d["mse"] - d_ref["mse"]) / d_ref["mse"], psnr=abs(d["psnr"] - d_ref["psnr"]), ssim=abs(d["ssim"] - d_ref["ssim"]),
+             lpips=abs(d["lpips"] - d_ref["lpips"]) / d_ref["lpips"],
+             img=float(np.abs(d["img"].astype(np.int32) - d_ref["img"].astype(np.int32)).max()),
+             depth=float(np.abs(d["depth"].astype(np.int32) - d_ref["depth"].astype(np.int32)).max()))
+    _report("eval_images", **e)
+    assert e["mse"] < 1e-4 and e["psnr"] < 1e-3 and e["ssim"] < 1e-5 and e["lpips"] < 1e-4 and e["img"] <= 1 and e["depth"] <= 1, e
+    assert d["depth_gt"].shape == d_ref["depth_gt"].shape and os.path.exists(str(tmp_path / "ours" / "img_out" / "0001.png"))
+
+
+def test_render_visdata_vs_live_reference(tmp_path):
+    """Trainer.render_visdata (model/training.py:100-163, nope_nerf view): uint8 frame of the reference's 1024-pixel chunk loop against
+    the single-call drop-in; files written with the reference's names"""
+    import nope_nerf_b200.model as mdl
+    from nope_nerf_b200 import ops
+    ops.set_default_engine("tc")
+    H, W, V = 48, 64, 4
+    cfg = RH.load_default_cfg()
+    cfg["training"]["vis_geo"] = False                                 # the phong geometry view is SURVEY 8(f) rank 4
+    torch.manual_seed(22)
+    rig = RH.RefRig(cfg, V, "cuda")
+    state = _init_state(rig, V, 96)
+    data = _small_scene(H, W, V=V)
+    (tmp_path / "ref").mkdir(); (tmp_path / "ours").mkdir()
+    img_ref = rig.trainer.render_visdata(data, (H, W), 0, str(tmp_path / "ref"))
+    trainer, net, pose, dist, model = _ours(cfg, V, state)
+    img = trainer.render_visdata(data, (H, W), 0, str(tmp_path / "ours"))
+    diff = int(np.abs(img.astype(np.int32) - img_ref.astype(np.int32)).max())
+    _report("render_visdata", max_uint8_diff=diff)
+    assert img.shape == img_ref.shape == (H, W, 3) and diff <= 1, diff
+    for f in ("0001_img.png", "0001_depth.png"):
+        assert os.path.exists(str(tmp_path / "ours" / f)) and os.path.exists(str(tmp_path / "ref" / f)), f

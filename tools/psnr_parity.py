@@ -55,7 +55,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=2000); ap.add_argument("--seeds", type=int, default=3)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "psnr_parity.json"))
+    ap.add_argument("--arms", default="eager,graph", help="comma list of: eager, graph, eager_simt (exact-fp32 engine), eager_exact (bf16 hi|lo "
+                    "weight-gradient planes), eager_torchadam (torch.optim.Adam.step instead of the fused one), graph_exact")
     a = ap.parse_args()
+    ARMS = {"eager": dict(use_cuda_graph=False, pixel_sampler="randperm"), "graph": dict(),
+            "eager_simt": dict(use_cuda_graph=False, pixel_sampler="randperm", _engine="simt"),
+            "eager_exact": dict(use_cuda_graph=False, pixel_sampler="randperm", _wgrad="exact"),
+            "graph_exact": dict(_wgrad="exact"),
+            "eager_torchadam": dict(use_cuda_graph=False, pixel_sampler="randperm", fused_adam=False)}
+    arms = [(n, dict(ARMS[n])) for n in a.arms.split(",")]
     assert RH.available(), "oracle/_ref missing (tools/vendor_ref.py)"
     dev = torch.device("cuda")
     H, W, hd, wd, V, N, S = 60, 80, 60, 80, 6, 512, 64
@@ -115,7 +123,10 @@ def main():
                       "train_psnr_last500": float(-10 * np.log10(np.mean(l2[-500:])))}
         del rig
         # ---- product, two modes ----
-        for arm, kw in (("eager", dict(use_cuda_graph=False, pixel_sampler="randperm")), ("graph", dict())):
+        for arm, kw0 in arms:
+            kw = dict(kw0)
+            from nope_nerf_b200 import ops as _ops
+            _ops.set_default_engine(kw.pop("_engine", "tc")); _ops.set_wgrad_precision(kw.pop("_wgrad", "fp16"))
             pcfg = json.loads(json.dumps(cfg)); pcfg["extract_images"] = {"resolution": (H, W)}
             net = mdl.OfficialStaticNerf(pcfg)
             net.load_state_dict({k: v.clone() for k, v in init["net"].items()})
@@ -157,7 +168,7 @@ def main():
             "psnr": "mean over all views and the checkpoints at steps %s" % sorted(eval_at),
             "ref_psnr_mean": float(refs.mean()), "ref_psnr_seed_std": float(refs.std(ddof=1)) if len(refs) > 1 else None,
             "ref_train_psnr_last500_mean": float(np.mean([r["ref"]["train_psnr_last500"] for r in results]))}
-    for arm in ("eager", "graph"):
+    for arm, _ in arms:
         d = np.array([r[arm]["dpsnr_vs_ref_db"] for r in results]); dt = np.array([r[arm]["dtrain_psnr_vs_ref_db"] for r in results])
         summ[arm] = {"dpsnr_mean_db": float(d.mean()), "dpsnr_standard_error_db": se(d), "dpsnr_per_seed_db": [round(float(x), 3) for x in d],
                      "psnr_mean": float(np.mean([r[arm]["psnr_mean"] for r in results])),

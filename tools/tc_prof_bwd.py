@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ["NNB_CUDA_GRAPH"] = "0"
 import bench
 from nope_nerf_b200 import _lib as L
-a = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", engine="tc", no_cpu_baseline=True)
+a = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", engine="tc", no_cpu_baseline=True, scaling="weak")
 bench.run_ours(a)
 buf = (C.c_ulonglong * (148 * 16))()
 L.lib.nnb_debug_dgprof(buf)
