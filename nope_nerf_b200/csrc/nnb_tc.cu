@@ -79,11 +79,15 @@ __global__ void tc_prep_weights(const float* __restrict__ w, unsigned char* __re
 #ifdef NNB_TC_PROFILE
 __device__ unsigned long long g_tcprof[148][8];
 __device__ unsigned long long g_tcprof2[148][8];
+// timeline of ONE tile (CTA 0, its 4th tile): [0..63] MMA thread, [64..255] epilogue thread (warp 2 lane 0); raw clock64 values
+__device__ unsigned long long g_tctrace[256];
+#define TRACE(cond, idx) do { if ((cond) && blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_tctrace[idx] = clock64(); } while (0)
 #define PROF_T0() unsigned long long _t0 = clock64()
 #define PROF_ADD(slot) do { unsigned long long _t1 = clock64(); _pacc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
 #else
 #define PROF_T0()
 #define PROF_ADD(slot)
+#define TRACE(cond, idx)
 #endif
 
 struct TcStash {   // fp32 [sample][feature] stash (layout of nnb_simt.cu) and, with NNB_TCBWD, operand planes + ReLU bitmasks
@@ -168,10 +172,16 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ====================================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop converged (every lane polls the barriers, all values are warp-uniform); the tcgen05.mma /
+    // tcgen05.commit instructions are issued by the one lane elect.sync picks, so ptxas emits them under a uniform predicate
+    // instead of wrapping each in a divergence-election loop (6 extra instructions per MMA when the code sat under `lane == 0`).
+    {
       uint32_t slot = 0, phase = 0;
-      const uint32_t a_hi = smem_u32(smem + SM_AHI), a_lo = smem_u32(smem + SM_ALO);
-      const uint32_t e_hi = smem_u32(smem + SM_EHI), e_lo = smem_u32(smem + SM_ELO);
+      // descriptor low words of the operand buffers (tc_stage6: everything else is an addition)
+      const uint32_t a_hi0 = desc_lo(smem_u32(smem + SM_AHI)), a_lo0 = desc_lo(smem_u32(smem + SM_ALO));
+      const uint32_t e_hi0 = desc_lo(smem_u32(smem + SM_EHI)), e_lo0 = desc_lo(smem_u32(smem + SM_ELO));
+      const uint32_t w_lo0 = desc_lo(smem_u32(smem + SM_W));
+      const uint32_t bar_full0 = BAR(B_FULL), bar_empty0 = BAR(B_EMPTY), bar_aready0 = BAR(B_AREADY);
       int tv = 0;   // number of VALID tiles processed so far (phase bookkeeping of the per-tile barriers)
 #ifdef NNB_TC_PROFILE
       unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -182,15 +192,15 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           for (int s = 0; s < N_STAGES; ++s) {
             mbar_wait(BAR(B_FULL + slot), phase);
             tc_fence_after();
-            if (CL == 1) tc_commit(BAR(B_EMPTY + slot)); else tc_commit_mc(BAR(B_EMPTY + slot), cmask);
+            if (CL == 1) tc_commit_elect(BAR(B_EMPTY + slot)); else tc_commit_mc_elect(BAR(B_EMPTY + slot), cmask);
             if (++slot == NST) { slot = 0; phase ^= 1; }
           }
           continue;
         }
         const uint32_t idesc = make_idesc(128, 128);
         for (int g = 0; g < N_GEMM; ++g) {
-          const int e_ksteps = (g == 0 || g == 4) ? 4 : 0;        // K-steps fed by the encoding operand E (shared memory)
-          const int a_ksteps = (g == 0) ? 0 : 16;                 // K-steps fed by the previous layer's output
+          const int e_stages = (g == 0 || g == 4) ? 2 : 0;        // weight stages (two K-steps each) fed by the encoding operand E
+          const bool has_a = (g != 0);                            // 8 stages fed by the previous layer's output
           const bool a_tmem = (g & 1) == 0;                       // even layers read A from tensor memory (written by the odd layer before)
           const int nhalf = (g == 9) ? 1 : 2;
           for (int h = 0; h < nhalf; ++h) {
@@ -199,53 +209,46 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             mbar_wait(BAR(B_ACCEMPTY + h), (use & 1u) ^ 1u);      // the epilogue of the previous layer has drained this half accumulator
             tc_fence_after();
             PROF_ADD(0);
+            TRACE(tv == 3, (g * 2 + h) * 3);
             const uint32_t d_tmem = tmem_base + h * 128;
             if (g == 0 && h == 0) { mbar_wait(BAR(B_EREADY), (uint32_t)tv & 1u); tc_fence_after(); }
             PROF_ADD(1);
             uint32_t acc = 0;
             uint32_t full_ok = mbar_probe(BAR(B_FULL + slot), phase);    // probe early: its latency hides under the other waits
-            for (int ks = 0; ks < e_ksteps + a_ksteps; ks += 2) {       // one 16 KB weight stage = two K-steps
-              uint64_t aL0, aH0, aL1, aH1;
-              bool ts = false;
-              if (ks < e_ksteps) {
-                aH0 = make_desc(e_hi + ks * 4096, 2048, 128); aL0 = make_desc(e_lo + ks * 4096, 2048, 128);
-                aH1 = make_desc(e_hi + (ks + 1) * 4096, 2048, 128); aL1 = make_desc(e_lo + (ks + 1) * 4096, 2048, 128);
-              } else {
-                const int ka = ks - e_ksteps;
-                if ((ka & 3) == 0 && h == 0) {  // first K-step of a 64-column block of A: wait for the previous layer's epilogue (half 1 re-reads)
-                  const uint32_t au = (uint32_t)tv * 9u + (uint32_t)(g - 1);
-                  mbar_wait(BAR(B_AREADY + (ka >> 2)), au & 1u);
-                  tc_fence_after();
-                }
-                if (a_tmem) {
-                  ts = true;
-                  aH0 = tmem_base + TM_AHI + ka * 8; aL0 = tmem_base + TM_ALO + ka * 8; aH1 = aH0 + 8; aL1 = aL0 + 8;
-                } else {
-                  aH0 = make_desc(a_hi + ka * 4096, 2048, 128); aL0 = make_desc(a_lo + ka * 4096, 2048, 128);
-                  aH1 = make_desc(a_hi + (ka + 1) * 4096, 2048, 128); aL1 = make_desc(a_lo + (ka + 1) * 4096, 2048, 128);
-                }
-              }
-              PROF_ADD(2);
-              if (!full_ok) mbar_wait(BAR(B_FULL + slot), phase);
+            // one weight stage: wait (rarely) for its bytes, six MMAs, release; descriptors are additions to precomputed low words
+            auto stage = [&](bool ts, uint32_t aL, uint32_t aH) {
+              if (!full_ok) mbar_wait(bar_full0 + 8u * slot, phase);
               tc_fence_after();
-              PROF_ADD(3);
-              const uint32_t wb = smem_u32(smem + SM_W + slot * STAGE_BYTES);   // [hi: k-octet 0..3][128][8] | [lo: ...], 4096 B per K-step
-              const uint64_t bH0 = make_desc(wb, 2048, 128), bL0 = make_desc(wb + 8192, 2048, 128);
-              const uint64_t bH1 = make_desc(wb + 4096, 2048, 128), bL1 = make_desc(wb + 8192 + 4096, 2048, 128);
+              const uint32_t wb = w_lo0 + slot * (STAGE_BYTES >> 4);
               const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
-              if (ts) full_ok = tc_stage_mma6<CL, true>(d_tmem, aL0, aH0, aL1, aH1, bH0, bL0, bH1, bL1, idesc, acc, BAR(B_EMPTY + slot), cmask, BAR(B_FULL + nslot), nphase);
-              else full_ok = tc_stage_mma6<CL, false>(d_tmem, aL0, aH0, aL1, aH1, bH0, bL0, bH1, bL1, idesc, acc, BAR(B_EMPTY + slot), cmask, BAR(B_FULL + nslot), nphase);
-              acc = 1u;
-              if (++slot == NST) { slot = 0; phase ^= 1; }
-              PROF_ADD(4);
+              if (ts) full_ok = tc_stage6<CL, true>(d_tmem, aL, aH, wb, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              else full_ok = tc_stage6<CL, false>(d_tmem, aL, aH, wb, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              acc = 1u; slot = nslot; phase = nphase;
+            };
+            for (int st = 0; st < e_stages; ++st) stage(false, e_lo0 + st * 512, e_hi0 + st * 512);
+            if (has_a) {
+              const uint32_t au = ((uint32_t)tv * 9u + (uint32_t)(g - 1)) & 1u;
+              const uint32_t aL = a_tmem ? tmem_base + TM_ALO : a_lo0, aH = a_tmem ? tmem_base + TM_AHI : a_hi0;
+              const uint32_t a_st = a_tmem ? 16u : 512u;         // two K-steps: 16 tensor-memory columns | 8192 B of shared memory
+#pragma unroll
+              for (int st = 0; st < 8; ++st) {
+                if ((st & 1) == 0 && h == 0) {   // first K-step of a 64-column block of A: wait for the previous layer's epilogue (half 1 re-reads)
+                  mbar_wait(bar_aready0 + 8u * (st >> 1), au);
+                  tc_fence_after();
+                  TRACE(tv == 3 && st == 6, (g * 2 + h) * 3 + 1);      // last A block of the layer has arrived
+                }
+                stage(a_tmem, aL + st * a_st, aH + st * a_st);
+              }
             }
-            tc_commit(BAR(B_ACCFULL + h));
+            PROF_ADD(4);
+            tc_commit_elect(BAR(B_ACCFULL + h));
+            TRACE(tv == 3, (g * 2 + h) * 3 + 2);
           }
         }
         ++tv;
       }
 #ifdef NNB_TC_PROFILE
-      if (blockIdx.x < 148) { for (int i = 0; i < 5; ++i) g_tcprof[blockIdx.x][i] = _pacc[i]; g_tcprof[blockIdx.x][5] = clock64() - _tstart; g_tcprof[blockIdx.x][6] = tv; }
+      if (lane == 0 && blockIdx.x < 148) { for (int i = 0; i < 5; ++i) g_tcprof[blockIdx.x][i] = _pacc[i]; g_tcprof[blockIdx.x][5] = clock64() - _tstart; g_tcprof[blockIdx.x][6] = tv; }
 #endif
     }
   } else {
@@ -405,6 +408,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
           mbar_wait(BAR(B_ACCFULL + h), use & 1u);
           tc_fence_after();
           PROF_ADD(1);
+          TRACE(t == 3 && warp == 2 && lane == 0, 64 + (g * 2 + h) * 8);
 #pragma unroll 1
           for (int ci = 0; ci < 2; ++ci) {
             const int cb = 4 * h + 2 * ci + half;          // 32-column chunk of the layer output; A block of the next layer = cb >> 1
@@ -428,11 +432,14 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
               mbar_arrive(BAR(B_AREADY + (cb >> 1)));     // 256 arrivals (both thread halves) complete the block
               PROF_ADD(5);
             }
+            TRACE(t == 3 && warp == 2 && lane == 0, 64 + (g * 2 + h) * 8 + 1 + ci * 2);
             if (need2) side_work(cb, v, mw, hw);
+            TRACE(t == 3 && warp == 2 && lane == 0, 64 + (g * 2 + h) * 8 + 2 + ci * 2);
           }
           tc_fence_before();
           mbar_arrive(BAR(B_ACCEMPTY + h));
           PROF_ADD(6);
+          TRACE(t == 3 && warp == 2 && lane == 0, 64 + (g * 2 + h) * 8 + 5);
         }
       }
       // ---- heads + per-sample record (half 1 hands its partial dot products to half 0) ----
@@ -495,6 +502,9 @@ cudaError_t upload_stage_table() {
 #ifdef NNB_TC_PROFILE
 extern "C" int nnb_debug_tcprof(unsigned long long* host148x8) {
   return (int)cudaMemcpyFromSymbol(host148x8, g_tcprof, sizeof(unsigned long long) * 148 * 8);
+}
+extern "C" int nnb_debug_tctrace(unsigned long long* host256) {
+  return (int)cudaMemcpyFromSymbol(host256, g_tctrace, sizeof(unsigned long long) * 256);
 }
 extern "C" int nnb_debug_tcprof2(unsigned long long* host148x8) {
   return (int)cudaMemcpyFromSymbol(host148x8, g_tcprof2, sizeof(unsigned long long) * 148 * 8);

@@ -18,6 +18,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef NNB_NO_WAIT_HINT
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -26,6 +36,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}"
       ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware instead of spinning
+#endif
 }
 // non-blocking probe: lets the caller overlap the ~110-cycle barrier round trip with other work
 __device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
@@ -45,6 +56,13 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit issued by ONE elected lane of a converged warp (the whole MMA warp runs the issue loop, see tc_stage6)
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc_elect(uint32_t bar, uint16_t mask) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -364,6 +382,78 @@ __device__ __forceinline__ uint32_t tc_stage_mma6(uint32_t d_tmem, uint64_t a_lo
         : "=r"(ok)
         : "r"(d_tmem), "r"(t_lo0), "r"(t_hi0), "r"(t_lo1), "r"(t_hi1), "l"(b_hi0), "l"(b_lo0), "l"(b_hi1), "l"(b_lo1), "r"(idesc), "r"(acc),
           "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "r"((uint32_t)CL), "h"(cmask)
+        : "memory");
+  }
+  return ok;
+}
+// ---- lean issue path -------------------------------------------------------------------------------------------------
+// One thread issues every MMA of a CTA; measured (tools/micro/mma_commit.cu) it sustains one tcgen05.mma per ~64 cycles only if
+// almost nothing else runs between them: building eight 64-bit descriptors per stage with shifts and masks made the issue loop,
+// not the tensor pipe, the bottleneck (130-190 cycles per MMA).  All operands here use LBO = 2048 B, SBO = 128 B, version 1, so
+// a descriptor is {low word = (addr >> 4) | (128 << 16), high word = DESC_HI}: the thread only ADDS to precomputed low words.
+constexpr uint32_t DESC_HI = 8u | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (128u << 16); }
+// Two K-steps of one 128-column half against one 16 KB weight stage ([hi: K-step 0 | K-step 1][lo: K-step 0 | K-step 1], 4096 B each):
+// probe of the next stage's barrier, six MMAs, release of the stage; the second K-step's operands are +256 descriptor units (A in
+// shared memory) or +8 tensor-memory columns (A in tensor memory, TS = true).
+template <int CL, bool TS>
+__device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint32_t aH, uint32_t wb, uint32_t idesc, uint32_t acc, uint32_t empty_bar,
+                                              uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
+  uint32_t ok;
+  if (!TS) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, e, ct, cm;\n\t.reg .b32 x;\n\t.reg .b64 al0, ah0, al1, ah1, bh0, bl0, bh1, bl1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 al0, {%2, %11};\n\t mov.b64 ah0, {%3, %11};\n\t"
+        "add.u32 x, %2, 256;\n\t mov.b64 al1, {x, %11};\n\t add.u32 x, %3, 256;\n\t mov.b64 ah1, {x, %11};\n\t"
+        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, 256;\n\t mov.b64 bh1, {x, %11};\n\t"
+        "add.u32 x, %4, 512;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, %4, 768;\n\t mov.b64 bl1, {x, %11};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al0, bh0, %5, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bl0, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bh0, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al1, bh1, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah1, bl1, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah1, bh1, %5, t;\n\t"
+        "setp.eq.u32 t, %12, 1;\n\t"
+        "and.pred ct, e, t;\n\t"
+        "not.pred t, t;\n\t"
+        "and.pred cm, e, t;\n\t"
+        "@ct tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+        "@cm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %10;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ok)
+        : "r"(d_tmem), "r"(aL), "r"(aH), "r"(wb), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask),
+          "r"(DESC_HI), "r"((uint32_t)CL)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, e, ct, cm;\n\t.reg .b32 x, al1, ah1;\n\t.reg .b64 bh0, bl0, bh1, bl1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "add.u32 al1, %2, 8;\n\t add.u32 ah1, %3, 8;\n\t"
+        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, 256;\n\t mov.b64 bh1, {x, %11};\n\t"
+        "add.u32 x, %4, 512;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, %4, 768;\n\t mov.b64 bl1, {x, %11};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], bh0, %5, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bl0, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bh0, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [al1], bh1, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bl1, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bh1, %5, t;\n\t"
+        "setp.eq.u32 t, %12, 1;\n\t"
+        "and.pred ct, e, t;\n\t"
+        "not.pred t, t;\n\t"
+        "and.pred cm, e, t;\n\t"
+        "@ct tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+        "@cm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %10;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ok)
+        : "r"(d_tmem), "r"(aL), "r"(aH), "r"(wb), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask),
+          "r"(DESC_HI), "r"((uint32_t)CL)
         : "memory");
   }
   return ok;

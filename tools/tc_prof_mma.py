@@ -34,3 +34,15 @@ for stash in (False, True):
     print("  epilogue thread (warp 2 lane 0), cycles per tile")
     for i, n in enumerate(names2):
         print("    %-22s %10.0f" % (n, (b[:, i] / np.maximum(a[:, 6], 1)).mean()))
+
+    # ---- timeline of CTA 0's 4th tile (cycles relative to the first event) ----
+    tb = (C.c_ulonglong * 256)()
+    if hasattr(L.lib, "nnb_debug_tctrace") and L.lib.nnb_debug_tctrace(tb) == 0:
+        tr = np.array(tb[:], dtype=np.float64)
+        t0 = tr[tr > 0].min() if (tr > 0).any() else 0
+        rel = lambda i: (tr[i] - t0) if tr[i] > 0 else float("nan")
+        print("  timeline (CTA 0, tile 3; cycles):  layer.half | MMA: start, lastA, issued | EPI: accfull, c0 arrive, c0 side, c1 arrive, c1 side, accempty")
+        for g in range(10):
+            for h in range(2 if g < 9 else 1):
+                k = (g * 2 + h) * 3; e = 64 + (g * 2 + h) * 8
+                print("    %d.%d | %7.0f %7.0f %7.0f | %7.0f %7.0f %7.0f %7.0f %7.0f %7.0f" % (g, h, rel(k), rel(k + 1), rel(k + 2), rel(e), rel(e + 1), rel(e + 2), rel(e + 3), rel(e + 4), rel(e + 5)))
