@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
               tc_fence_after();
               const uint32_t wb = w_lo0 + slot * (STAGE_BYTES >> 4);
               const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
-              if (ts) full_ok = tc_stage6<CL, true>(d_tmem, aL, aH, wb, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
-              else full_ok = tc_stage6<CL, false>(d_tmem, aL, aH, wb, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              if (ts) full_ok = tc_stage6<CL, true>(d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              else full_ok = tc_stage6<CL, false>(d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
               acc = 1u; slot = nslot; phase = nphase;
             };
             for (int st = 0; st < e_stages; ++st) stage(false, e_lo0 + st * 512, e_hi0 + st * 512);

@@ -25,20 +25,25 @@ using namespace tcu;
 
 constexpr int TILE = 128;
 constexpr int NST = 3;
-constexpr int STAGE_BYTES = 16384;
+constexpr int STAGE_BYTES = 16384;          // 128 rows x 32 reduction indices x (hi + lo) bf16
 constexpr int N_POS = 11;
 struct StageDescT { int w_off, ldw, n0, nvalid, kcol0, kvalid, nrows, img_off; };
-constexpr int N_STAGES_T = 8 + 16 * 8 + 16 + 16;     // 168
+// one stage = 32 reduction indices (two K-steps) x `nrows` output rows (128 = one half of a 256-wide GEMM, 64 = the encoding slices)
+constexpr int N_STAGES_T = 2 * 4 + 8 * 2 * 8 + 8 + 8;     // pos0 (K = 128), 8 full positions, pos5, pos10  = 152
 __constant__ StageDescT c_stages_t[N_STAGES_T];
-constexpr size_t IMG_T_BYTES = (size_t)(8 + 16 * 8) * STAGE_BYTES + 32 * (STAGE_BYTES / 4);
+constexpr size_t IMG_T_BYTES = (size_t)(2 * 4 + 8 * 2 * 8) * STAGE_BYTES + 16 * (STAGE_BYTES / 2);
 
 // position table of the dgrad chain (see header comment of tc_dgrad)
-//   N      : output width of the GEMM (256 | 64)
+//   N      : output width of the GEMM (256 = two 128-column halves | 64)
 //   ksteps : reduction length / 16
-//   aver   : which version of the A operand it reads (0 = prologue, k = written by the k-th A-writing epilogue)
+//   aver   : which version of the A operand it reads (0 = prologue, k = written by the k-th A-writing epilogue); EVEN versions live in
+//            tensor memory (.ts MMA form), ODD versions in shared memory, so an epilogue never writes the medium the running MMAs read
+//   ord1   : ordinal of the position among those that use the second half accumulator (barrier phase bookkeeping)
 __constant__ int c_pos_N[N_POS] = {256, 256, 256, 256, 256, 64, 256, 256, 256, 256, 64};
 __constant__ int c_pos_ksteps[N_POS] = {8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16};
 __constant__ int c_pos_aver[N_POS] = {0, 1, 2, 3, 4, 5, 5, 6, 7, 8, 9};
+__constant__ int c_pos_ord1[N_POS] = {0, 1, 2, 3, 4, 0, 5, 6, 7, 8, 0};
+constexpr uint32_t TM_AHI = 256, TM_ALO = 384;   // tensor-memory columns of the even A versions (hi | lo bf16, two k per column)
 
 constexpr int DG_AHI = 0, DG_ALO = 65536, DG_W = 131072, DG_GENC = DG_W + NST * STAGE_BYTES;   // 180224
 constexpr int DG_SMALL = DG_GENC + 64 * 128 * 4;                                                   // 212992
@@ -53,9 +58,9 @@ enum { D_FULL = 0, D_EMPTY = NST, D_AREADY = 2 * NST, D_ACCFULL = 2 * NST + 4, D
 //      element (row k, red nn) = W[(n0+nn) * ldw + kcol0 + k]
 __global__ void tc_prep_weights_T(const float* __restrict__ w, unsigned char* __restrict__ img) {
   const StageDescT sd = c_stages_t[blockIdx.x];
-  unsigned char* hi = img + sd.img_off;
-  unsigned char* lo = hi + sd.nrows * 32;
-  for (int idx = threadIdx.x; idx < sd.nrows * 2; idx += blockDim.x) {
+  unsigned char* hi = img + sd.img_off;          // [reduction octet 0..3][nrows][8] bf16
+  unsigned char* lo = hi + sd.nrows * 64;
+  for (int idx = threadIdx.x; idx < sd.nrows * 4; idx += blockDim.x) {
     int k = idx % sd.nrows, no = idx / sd.nrows;
     float v[8];
 #pragma unroll
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
       uint32_t slot = 0, phase = 0;
       for (int t = 0; t < my_tiles; ++t)
         for (int s = 0; s < N_STAGES_T; ++s) {
-          const int bytes = c_stages_t[s].nrows * 64;
+          const int bytes = c_stages_t[s].nrows * 128;
           mbar_wait(BAR(D_EMPTY + slot), phase ^ 1);
           mbar_expect_tx(BAR(D_FULL + slot), bytes);
           if (CL == 1) bulk_g2s(smem_u32(smem + DG_W + slot * STAGE_BYTES), wimg + c_stages_t[s].img_off, bytes, BAR(D_FULL + slot));
@@ -188,9 +193,12 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the WHOLE warp runs the loop converged, one elect.sync lane issues (see tc_stage6 / nnb_tc.cu)
+    {
       uint32_t slot = 0, phase = 0;
-      const uint32_t a_hi = smem_u32(smem + DG_AHI), a_lo = smem_u32(smem + DG_ALO);
+      const uint32_t a_hi0 = desc_lo(smem_u32(smem + DG_AHI)), a_lo0 = desc_lo(smem_u32(smem + DG_ALO));
+      const uint32_t w_addr16 = (smem_u32(smem + DG_W) >> 4) & 0x3FFFu;
+      const uint32_t bar_full0 = BAR(D_FULL), bar_empty0 = BAR(D_EMPTY), bar_aready0 = BAR(D_AREADY);
       int tv = 0;
 #ifdef NNB_TC_PROFILE
       unsigned long long _dp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -201,52 +209,54 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           for (int s = 0; s < N_STAGES_T; ++s) {
             mbar_wait(BAR(D_FULL + slot), phase);
             tc_fence_after();
-            if (CL == 1) tc_commit(BAR(D_EMPTY + slot)); else tc_commit_mc(BAR(D_EMPTY + slot), cmask);
+            if (CL == 1) tc_commit_elect(BAR(D_EMPTY + slot)); else tc_commit_mc_elect(BAR(D_EMPTY + slot), cmask);
             if (++slot == NST) { slot = 0; phase ^= 1; }
           }
           continue;
         }
         const int t = tv++;
         for (int pos = 0; pos < N_POS; ++pos) {
-          const int buf = pos & 1;
-          const uint32_t use = buf ? (uint32_t)t * 5u + (uint32_t)(pos >> 1) : (uint32_t)t * 6u + (uint32_t)(pos >> 1);
-          DGP_T0();
-          mbar_wait(BAR(D_ACCEMPTY + buf), (use & 1u) ^ 1u);
-          tc_fence_after();
-          DGP_ADD(0);
-          const int N = c_pos_N[pos], ksteps = c_pos_ksteps[pos];
-          const uint32_t d_tmem = tmem_base + buf * 256;
-          const uint32_t idesc = make_idesc_ex(128, N, 1, 1, 0, 0);   // A = gradients, B = transposed weights, both bf16 hi|lo, K-major
-          const uint32_t b_lbo = N * 16;
-          const uint32_t aver = (uint32_t)t * 10u + (uint32_t)c_pos_aver[pos];
-          uint32_t acc = 0;
-          uint32_t full_ok = mbar_probe(BAR(D_FULL + slot), phase);   // probe early: the barrier round trip hides under the other waits
-          for (int ks = 0; ks < ksteps; ++ks) {
-            if ((ks & 3) == 0 && pos != 6) {   // pos 6 re-reads the A version pos 5 already waited for
-              DGP_SKIP();
-              mbar_wait(BAR(D_AREADY + (ks >> 2)), aver & 1u);
-              tc_fence_after();
-              DGP_ADD(5 + pos);
-            }
-            DGP_SKIP();
-            if (!full_ok) mbar_wait(BAR(D_FULL + slot), phase);
+          const int N = c_pos_N[pos], nstage = c_pos_ksteps[pos] >> 1;
+          const int nhalf = (N == 256) ? 2 : 1, NH = (N == 256) ? 128 : 64;
+          const uint32_t idesc = make_idesc_ex(128, NH, 1, 1, 0, 0);   // A = gradients, B = transposed weights, both bf16 hi|lo, K-major
+          const uint32_t aver = ((uint32_t)t * 10u + (uint32_t)c_pos_aver[pos]) & 1u;
+          const bool a_tmem = (c_pos_aver[pos] & 1) == 0;
+          const uint32_t w_lo0 = w_addr16 | ((uint32_t)NH << 16);      // B tile: LBO = 16 * NH bytes between reduction octets
+          const uint32_t b_ks = (uint32_t)NH * 2u;                       // descriptor units between [hi K0 | hi K1 | lo K0 | lo K1]
+          const uint32_t aL0 = a_tmem ? tmem_base + TM_ALO : a_lo0, aH0 = a_tmem ? tmem_base + TM_AHI : a_hi0;
+          const uint32_t a_st = a_tmem ? 16u : 512u;                      // two K-steps: 16 tensor-memory columns | 8192 B of shared memory
+          for (int h = 0; h < nhalf; ++h) {
+            const uint32_t use = h ? (uint32_t)t * 9u + (uint32_t)c_pos_ord1[pos] : (uint32_t)t * 11u + (uint32_t)pos;
+            DGP_T0();
+            mbar_wait(BAR(D_ACCEMPTY + h), (use & 1u) ^ 1u);
             tc_fence_after();
-            DGP_ADD(1);
-            const uint32_t wb = smem_u32(smem + DG_W + slot * STAGE_BYTES);
-            const uint64_t dAh = make_desc(a_hi + ks * 4096, 2048, 128), dAl = make_desc(a_lo + ks * 4096, 2048, 128);
-            const uint64_t dBh = make_desc(wb, b_lbo, 128), dBl = make_desc(wb + N * 32, b_lbo, 128);
-            {
+            DGP_ADD(0);
+            const uint32_t d_tmem = tmem_base + h * 128;
+            uint32_t acc = 0;
+            uint32_t full_ok = mbar_probe(BAR(D_FULL + slot), phase);   // probe early: the barrier round trip hides under the other waits
+#pragma unroll 1
+            for (int st = 0; st < nstage; ++st) {
+              if ((st & 1) == 0 && pos != 6 && h == 0) {   // pos 6 and every second half re-read an A version already waited for
+                DGP_SKIP();
+                mbar_wait(bar_aready0 + 8u * (st >> 1), aver);
+                tc_fence_after();
+                DGP_ADD(5 + pos);
+              }
+              if (!full_ok) mbar_wait(bar_full0 + 8u * slot, phase);
+              tc_fence_after();
+              const uint32_t wb = w_lo0 + slot * (STAGE_BYTES >> 4);
               const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
-              full_ok = tc_stage_mma3<CL>(d_tmem, dAl, dAh, dBh, dBl, idesc, acc, BAR(D_EMPTY + slot), cmask, BAR(D_FULL + nslot), nphase);
+              if (a_tmem) full_ok = tc_stage6<CL, true>(d_tmem, aL0 + st * a_st, aH0 + st * a_st, wb, b_ks, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              else full_ok = tc_stage6<CL, false>(d_tmem, aL0 + st * a_st, aH0 + st * a_st, wb, b_ks, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              acc = 1u; slot = nslot; phase = nphase;
             }
-            acc = 1u;
-            if (++slot == NST) { slot = 0; phase ^= 1; }
+            DGP_ADD(1);
+            tc_commit_elect(BAR(D_ACCFULL + h));
           }
-          tc_commit(BAR(D_ACCFULL + buf));
         }
       }
 #ifdef NNB_TC_PROFILE
-      if (blockIdx.x < 148) { _dp[2] = (unsigned long long)(clock64() - _tstart); _dp[3] = tv; for (int i = 0; i < 16; ++i) g_dgprof[blockIdx.x][i] = _dp[i]; }
+      if (lane == 0 && blockIdx.x < 148) { _dp[2] = (unsigned long long)(clock64() - _tstart); _dp[3] = tv; for (int i = 0; i < 16; ++i) g_dgprof[blockIdx.x][i] = _dp[i]; }
 #endif
     }
   } else {
@@ -301,7 +311,12 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
             float x = gyc0 * s_small[jb * 8 + j] + gyc1 * s_small[128 + jb * 8 + j] + gyc2 * s_small[256 + jb * 8 + j];
             v[j] = ((mb >> j) & 1u) ? x : 0.f;
           }
-          split_store8_bf16_dual(v, A_hi + jb * 2048 + row * 16, A_lo + jb * 2048 + row * 16, gpl ? gpl + jb * 1024 : nullptr, gpl + 32768 + jb * 1024);
+          {   // A version 0 (g_yr, K = 128) goes to TENSOR memory: 8 values = 4 packed bf16 words per half, columns jb*4 ..
+            uint32_t hw4[4], lw4[4];
+            split8_bf16_words(v, hw4, lw4);
+            tc_st4(lane_addr + TM_AHI + jb * 4, hw4); tc_st4(lane_addr + TM_ALO + jb * 4, lw4);
+            if (gpl) { st_stream16(gpl + jb * 1024, make_uint4(hw4[0], hw4[1], hw4[2], hw4[3])); st_stream16(gpl + 32768 + jb * 1024, make_uint4(lw4[0], lw4[1], lw4[2], lw4[3])); }
+          }
           if (gpl16) stream8_f16_scaled(v, sc9, gpl16 + jb * 1024);
           if (wg16 && ji == 0) {   // max |dY| sample (one 8-column group per row is enough: the scale has 2^10 of headroom)
             float mx = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))), fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
@@ -310,14 +325,12 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
           }
           *reinterpret_cast<float4*>(dyr + jb * 8) = make_float4(v[0] * inv_gscale, v[1] * inv_gscale, v[2] * inv_gscale, v[3] * inv_gscale);
           *reinterpret_cast<float4*>(dyr + jb * 8 + 4) = make_float4(v[4] * inv_gscale, v[5] * inv_gscale, v[6] * inv_gscale, v[7] * inv_gscale);
-          if ((ji & 3) == 3) { fence_async_smem(); mbar_arrive(BAR(D_AREADY + (ji >> 2))); }   // block 0 / 1 of g_yr complete (256 arrivals)
+          if ((ji & 3) == 3) { tc_wait_st(); tc_fence_before(); mbar_arrive(BAR(D_AREADY + (ji >> 2))); }   // block 0 / 1 of g_yr complete (256 arrivals)
         }
       }
       mbar_arrive(BAR(D_AREADY + 2)); mbar_arrive(BAR(D_AREADY + 3));     // blocks 2,3 are empty in A version 0 (K = 128)
       // ---- chain ----
       for (int pos = 0; pos < N_POS; ++pos) {
-        const int buf = pos & 1;
-        const uint32_t use = buf ? (uint32_t)t * 5u + (uint32_t)(pos >> 1) : (uint32_t)t * 6u + (uint32_t)(pos >> 1);
         const bool writes_a = (pos != 5 && pos != 10);
         // mask layer: g_y_l = g_h_l * (h_l > 0) with l = 7 (pos1), 6,5,4 (pos2..4), 3 (pos6), 2,1,0 (pos7..9)
         const int mask_l = (pos == 1) ? 7 : (pos >= 2 && pos <= 4) ? 8 - pos : (pos == 6) ? 3 : (pos >= 7 && pos <= 9) ? 9 - pos : -1;
@@ -327,58 +340,81 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         if (mrow) {   // the forward stores column j of a chunk at bit 31 - j
           mq0 = __brev(__ldg(mrow + half)); mq1 = __brev(__ldg(mrow + 2 + half)); mq2 = __brev(__ldg(mrow + 4 + half)); mq3 = __brev(__ldg(mrow + 6 + half));
         }
-        mbar_wait(BAR(D_ACCFULL + buf), use & 1u);
-        tc_fence_after();
-        const int nch = (pos == 5 || pos == 10) ? 1 : 4;   // 32-column chunks handled by this half
         // A will hold: pos0 -> g_feat ; pos1 -> g_y7 ; pos2..4 -> g_y6..4 ; pos6 -> g_y3 ; pos7..9 -> g_y2..0
         const int di = (pos == 0) ? 8 : (pos == 1) ? 7 : (pos <= 4) ? 8 - pos : (pos == 6) ? 3 : 9 - pos;
         unsigned char* gpl = (write_dy && writes_a && !wg16) ? P.dyp[di] + (size_t)tile * PLANE_TILE_256 + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
         unsigned char* gpl16 = (write_dy && writes_a && wg16) ? P.dyp[di] + (size_t)tile * (PLANE_TILE_256 / 2) + (row >> 6) * 32768 + (row & 63) * 16 : nullptr;
         const float scd = s_wgscale[di];
+        const int nhalf = writes_a ? 2 : 1;
+        // the A version this epilogue writes is c_pos_aver[pos] + 1: odd -> shared memory, even -> tensor memory (the MMAs of THIS
+        // position read the other medium, so half 0 is converted while the tensor core still works on half 1)
+        const bool next_tmem = ((c_pos_aver[pos] + 1) & 1) == 0;
 #pragma unroll 1
-        for (int ci = 0; ci < nch; ++ci) {
-          const int cb = (nch == 1) ? half : 2 * ci + half;    // halves share each 64-column block (ready after one chunk time)
-          uint32_t r[32];
-          tc_ld32(lane_addr + buf * 256 + cb * 32, r);
-          float v[32];
-          const uint32_t mw = (ci == 0) ? mq0 : (ci == 1) ? mq1 : (ci == 2) ? mq2 : mq3;
+        for (int h = 0; h < nhalf; ++h) {
+          const uint32_t use = h ? (uint32_t)t * 9u + (uint32_t)c_pos_ord1[pos] : (uint32_t)t * 11u + (uint32_t)pos;
+          mbar_wait(BAR(D_ACCFULL + h), use & 1u);
+          tc_fence_after();
+          const int nci = writes_a ? 2 : 1;
+#pragma unroll 1
+          for (int ci = 0; ci < nci; ++ci) {
+            const int cb = writes_a ? 4 * h + 2 * ci + half : half;    // 32-column chunk; the two thread halves share each 64-column block
+            uint32_t r[32];
+            tc_ld32(lane_addr + cb * 32, r);
+            float v[32];
+            const int mk = cb >> 1;
+            const uint32_t mw = (mk == 0) ? mq0 : (mk == 1) ? mq1 : (mk == 2) ? mq2 : mq3;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (pos == 1) x = fmaf(g_s, s_small[384 + cb * 32 + j], x);
-            v[j] = ((mw >> j) & 1u) ? x : 0.f;
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (pos == 1) x = fmaf(g_s, s_small[384 + cb * 32 + j], x);
+              v[j] = ((mw >> j) & 1u) ? x : 0.f;
+            }
+            if (pos == 5) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s_genc[(cb * 32 + j) * 128 + row] = v[j];
+            } else if (pos == 10) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s_genc[(cb * 32 + j) * 128 + row] += v[j];
+            } else {
+              uint32_t hw[16], lw[16];
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) split8_bf16_words(v + kb * 8, hw + kb * 4, lw + kb * 4);
+              if (next_tmem) {
+                tc_st16(lane_addr + TM_AHI + cb * 16, hw); tc_st16(lane_addr + TM_ALO + cb * 16, lw);
+                tc_wait_st();
+                tc_fence_before();
+              } else {
+                store_words_smem(hw, lw, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16);
+                fence_async_smem();
+              }
+              mbar_arrive(BAR(D_AREADY + (cb >> 1)));
+              if (gpl) {     // bf16 hi|lo dY planes of the exact weight-gradient pass: the same words, streamed
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                  st_stream16(gpl + (cb * 4 + kb) * 1024, make_uint4(hw[kb * 4], hw[kb * 4 + 1], hw[kb * 4 + 2], hw[kb * 4 + 3]));
+                  st_stream16(gpl + 65536 + (cb * 4 + kb) * 1024, make_uint4(lw[kb * 4], lw[kb * 4 + 1], lw[kb * 4 + 2], lw[kb * 4 + 3]));
+                }
+              }
+              if (gpl16) {   // fp16 dY plane of the weight-gradient pass: after the MMA warp has been released
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) stream8_f16_scaled(v + kb * 8, scd, gpl16 + (cb * 4 + kb) * 1024);
+              }
+              if (wg16 && h == 0 && ci == 0) {   // max |dY_l| sample: this thread's first chunk (a quarter of the columns)
+                float mx = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+                const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+                if (lane == 0) atomicMax(&s_amax[di], mb);
+              }
+              if (write_dy) {   // bias gradient of this layer: db[n] = sum_m dY[m][n] (off the MMA's critical path)
+                const float cs = warp_colsum32(v, lane);
+                atomicAdd(&s_colsum[di * 256 + cb * 32 + lane], cs * inv_gscale);
+              }
+            }
           }
-          if (pos == 5) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s_genc[(cb * 32 + j) * 128 + row] = v[j];
-          } else if (pos == 10) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s_genc[(cb * 32 + j) * 128 + row] += v[j];
-          } else {
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb)
-              split_store8_bf16_dual(v + kb * 8, A_hi + (cb * 4 + kb) * 2048 + row * 16, A_lo + (cb * 4 + kb) * 2048 + row * 16,
-                                     gpl ? gpl + (cb * 4 + kb) * 1024 : nullptr, gpl + 65536 + (cb * 4 + kb) * 1024);
-            fence_async_smem(); mbar_arrive(BAR(D_AREADY + ci));
-            if (gpl16) {   // fp16 dY plane of the weight-gradient pass: after the MMA warp has been released
-#pragma unroll
-              for (int kb = 0; kb < 4; ++kb) stream8_f16_scaled(v + kb * 8, scd, gpl16 + (cb * 4 + kb) * 1024);
-            }
-            if (wg16 && ci == 0) {   // max |dY_l| sample: this thread's first chunk (a quarter of the columns)
-              float mx = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
-              const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
-              if (lane == 0) atomicMax(&s_amax[di], mb);
-            }
-            if (write_dy) {   // bias gradient of this layer: db[n] = sum_m dY[m][n] (off the MMA's critical path)
-              const float cs = warp_colsum32(v, lane);
-              atomicAdd(&s_colsum[di * 256 + cb * 32 + lane], cs * inv_gscale);
-            }
-          }
+          tc_fence_before();
+          mbar_arrive(BAR(D_ACCEMPTY + h));
         }
-        tc_fence_before();
-        mbar_arrive(BAR(D_ACCEMPTY + buf));
       }
       // ---- encoding adjoint (both halves' columns of g_enc are in shared memory): half 0 takes the raw coordinates and
       //      levels 0..4, half 1 levels 5..9; half 1 hands its partial sum over through its own (consumed) g_enc slots ----
@@ -934,15 +970,19 @@ cudaError_t upload_stage_table_t() {
   int s = 0, off = 0;
   auto add = [&](int w_off, int ldw, int n0, int nvalid, int kcol0, int kvalid, int nrows) {
     h[s] = StageDescT{w_off, ldw, n0, nvalid, kcol0, kvalid, nrows, off};
-    off += nrows * 64; ++s;
+    off += nrows * 128; ++s;
   };
-  for (int i = 0; i < 8; ++i) add(nnb::W_RGBH, 283, 16 * i, 128, 0, 256, 256);                 // pos0: g_feat = g_yr @ Wr[:, :256]
-  for (int i = 0; i < 16; ++i) add(nnb::W_FEAT, 256, 16 * i, 256, 0, 256, 256);                // pos1
-  for (int l = 7; l >= 5; --l) for (int i = 0; i < 16; ++i) add(nnb::w_off(l), 256, 16 * i, 256, 0, 256, 256);   // pos2..4
-  for (int i = 0; i < 16; ++i) add(nnb::w_off(4), 319, 16 * i, 256, 256, 319, 64);             // pos5: enc slice of layer 4
-  for (int i = 0; i < 16; ++i) add(nnb::w_off(4), 319, 16 * i, 256, 0, 256, 256);              // pos6
-  for (int l = 3; l >= 1; --l) for (int i = 0; i < 16; ++i) add(nnb::w_off(l), 256, 16 * i, 256, 0, 256, 256);   // pos7..9
-  for (int i = 0; i < 16; ++i) add(nnb::w_off(0), 63, 16 * i, 256, 0, 63, 64);                 // pos10
+  // per position: half 0 (output rows 0..127) then half 1 (rows 128..255); 32 reduction indices per stage
+  auto full = [&](int w_off, int ldw, int nred, int kvalid) {
+    for (int h = 0; h < 2; ++h) for (int i = 0; i < nred / 32; ++i) add(w_off, ldw, 32 * i, nred, 128 * h, kvalid, 128);
+  };
+  full(nnb::W_RGBH, 283, 128, 256);                                                            // pos0: g_feat = g_yr @ Wr[:, :256]
+  full(nnb::W_FEAT, 256, 256, 256);                                                            // pos1
+  for (int l = 7; l >= 5; --l) full(nnb::w_off(l), 256, 256, 256);                             // pos2..4
+  for (int i = 0; i < 8; ++i) add(nnb::w_off(4), 319, 32 * i, 256, 256, 319, 64);              // pos5: enc slice of layer 4
+  full(nnb::w_off(4), 319, 256, 256);                                                          // pos6
+  for (int l = 3; l >= 1; --l) full(nnb::w_off(l), 256, 256, 256);                             // pos7..9
+  for (int i = 0; i < 8; ++i) add(nnb::w_off(0), 63, 32 * i, 256, 0, 63, 64);                  // pos10
   if (s != N_STAGES_T || (size_t)off != IMG_T_BYTES) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemcpyToSymbol(c_stages_t, h, sizeof(h));
   if (e == cudaSuccess) g_table_t_ready = true;

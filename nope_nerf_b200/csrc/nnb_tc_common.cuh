@@ -157,6 +157,21 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tc_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// bf16 hi | lo split of 8 values as 4 + 4 packed words (even element in the low half)
+__device__ __forceinline__ void split8_bf16_words(const float* v, uint32_t* hw, uint32_t* lw) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<uint32_t*>(&hh);
+    float l0, l1;
+    f2_unpack(f2_sub(f2_pack(v[2 * i], v[2 * i + 1]), u2_pack(hb << 16, hb & 0xffff0000u)), l0, l1);   // bf16 -> f32 is a shift
+    __nv_bfloat162 ll = __floats2bfloat162_rn(l0, l1);
+    hw[i] = hb; lw[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // fp16 (saturating) of 8 values times a power-of-two scale, streamed to global memory: one plane of a NNB_WG16 dY operand
 __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
@@ -397,7 +412,7 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 
 // probe of the next stage's barrier, six MMAs, release of the stage; the second K-step's operands are +256 descriptor units (A in
 // shared memory) or +8 tensor-memory columns (A in tensor memory, TS = true).
 template <int CL, bool TS>
-__device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint32_t aH, uint32_t wb, uint32_t idesc, uint32_t acc, uint32_t empty_bar,
+__device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint32_t aH, uint32_t wb, uint32_t b_ks, uint32_t idesc, uint32_t acc, uint32_t empty_bar,
                                               uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
   uint32_t ok;
   if (!TS) {
@@ -409,8 +424,8 @@ __device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint
         "elect.sync _|e, 0xffffffff;\n\t"
         "mov.b64 al0, {%2, %11};\n\t mov.b64 ah0, {%3, %11};\n\t"
         "add.u32 x, %2, 256;\n\t mov.b64 al1, {x, %11};\n\t add.u32 x, %3, 256;\n\t mov.b64 ah1, {x, %11};\n\t"
-        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, 256;\n\t mov.b64 bh1, {x, %11};\n\t"
-        "add.u32 x, %4, 512;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, %4, 768;\n\t mov.b64 bl1, {x, %11};\n\t"
+        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, %13;\n\t mov.b64 bh1, {x, %11};\n\t"
+        "add.u32 x, x, %13;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, x, %13;\n\t mov.b64 bl1, {x, %11};\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al0, bh0, %5, p;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bl0, %5, t;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bh0, %5, t;\n\t"
@@ -426,7 +441,7 @@ __device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint
         "selp.u32 %0, 1, 0, q;\n\t}"
         : "=r"(ok)
         : "r"(d_tmem), "r"(aL), "r"(aH), "r"(wb), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask),
-          "r"(DESC_HI), "r"((uint32_t)CL)
+          "r"(DESC_HI), "r"((uint32_t)CL), "r"(b_ks)
         : "memory");
   } else {
     asm volatile(
@@ -436,8 +451,8 @@ __device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint
         "setp.eq.u32 t, 0, 0;\n\t"
         "elect.sync _|e, 0xffffffff;\n\t"
         "add.u32 al1, %2, 8;\n\t add.u32 ah1, %3, 8;\n\t"
-        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, 256;\n\t mov.b64 bh1, {x, %11};\n\t"
-        "add.u32 x, %4, 512;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, %4, 768;\n\t mov.b64 bl1, {x, %11};\n\t"
+        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, %13;\n\t mov.b64 bh1, {x, %11};\n\t"
+        "add.u32 x, x, %13;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, x, %13;\n\t mov.b64 bl1, {x, %11};\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], bh0, %5, p;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bl0, %5, t;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bh0, %5, t;\n\t"
@@ -453,7 +468,7 @@ __device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint
         "selp.u32 %0, 1, 0, q;\n\t}"
         : "=r"(ok)
         : "r"(d_tmem), "r"(aL), "r"(aH), "r"(wb), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask),
-          "r"(DESC_HI), "r"((uint32_t)CL)
+          "r"(DESC_HI), "r"((uint32_t)CL), "r"(b_ks)
         : "memory");
   }
   return ok;
