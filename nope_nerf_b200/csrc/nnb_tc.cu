@@ -7,6 +7,10 @@
 //                 (M=128, N=256|128, K=16) with BOTH operands from shared memory; every logical
 //                 product runs as three MMAs a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (split-fp16, 22-bit
 //                 operands, fp32 accumulation in TMEM) so results match the fp32 reference
+//   warps 10..13: prologue         - thread = sample row of the NEXT tile: ray generation, prior gather, sampling, the 63-column
+//                 positional encoding -> E operand (+ its plane / stash), direction encoding -> per-ray bias of rgb_layers.0;
+//                 runs one tile ahead of the epilogue (the E operand is free once layer 4's MMAs have completed), so the
+//                 30 sincosf per sample never sit between two tiles of the tensor pipe
 //   warps 2..9  : epilogue         - two warps per TMEM lane quarter (thread = sample row, the two warps take
 //                 alternate 32-column chunks): tcgen05.ld of the accumulator, bias + ReLU, re-split into
 //                 hi/lo halves written IN PLACE as the next layer's A operand (canonical no-swizzle
@@ -49,11 +53,12 @@ constexpr int SM_AHI = 0, SM_ALO = 65536, SM_EHI = 131072, SM_ELO = 147456, SM_W
 constexpr int SM_BIAS = SM_W + NST * STAGE_BYTES;             // 212992
 constexpr int BIAS_FLOATS = 8 * 256 + 256 + 256 + 384 + 4;    // trunk, feat, w_sigma, W_rgb, (b_sigma, b_rgb[3])
 constexpr int SM_RAYB = SM_BIAS + ((BIAS_FLOATS * 4 + 127) / 128) * 128;
-constexpr int SM_PART = SM_RAYB + (4 * 128 + 4 * 32) * 4;   // per-ray bias [4][128] + direction-encoding staging [4][32]
+constexpr int RAYB_FLOATS = 4 * 128 + 4 * 32;                 // per-ray bias [4][128] + direction-encoding staging [4][32]
+constexpr int SM_PART = SM_RAYB + 2 * RAYB_FLOATS * 4;      // two buffers: the prologue warps run one tile ahead of the epilogue
 constexpr int SM_BAR = SM_PART + 128 * 4 * 4;                // head partial sums / exchange buffer
 constexpr int SM_TOTAL = SM_BAR + 32 * 8 + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
-enum { B_FULL = 0, B_EMPTY = NST, B_AREADY = 2 * NST, B_EREADY = 2 * NST + 4, B_ACCFULL = 2 * NST + 5, B_ACCEMPTY = 2 * NST + 7, B_COUNT = 2 * NST + 9 };
+enum { B_FULL = 0, B_EMPTY = NST, B_AREADY = 2 * NST, B_EREADY = 2 * NST + 4, B_ACCFULL = 2 * NST + 5, B_ACCEMPTY = 2 * NST + 7, B_EFREE = 2 * NST + 9, B_COUNT = 2 * NST + 10 };
 constexpr uint32_t TM_AHI = 256, TM_ALO = 384;   // tensor-memory columns of the even layers' A operand
 
 using namespace tcu;
@@ -105,7 +110,7 @@ __device__ __forceinline__ void row_geometry_tc(const nnb_render_args& a, size_t
 }
 
 template <int CL>   // CL = thread-block cluster size (1 | 2 | 4): CTAs of a cluster share every weight stage via multicast
-__global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const unsigned char* __restrict__ wimg, SampleRec* __restrict__ recs,
+__global__ void __launch_bounds__(448, 1) tc_field_fwd(nnb_render_args a, const unsigned char* __restrict__ wimg, SampleRec* __restrict__ recs,
                                                         TcStash st, size_t M, int n_tiles, int stash) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), CL); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(B_AREADY + i), 256);
-    mbar_init(BAR(B_EREADY), 256);
+    mbar_init(BAR(B_EREADY), 128);
+    mbar_init(BAR(B_EFREE), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             }
             PROF_ADD(4);
             tc_commit_elect(BAR(B_ACCFULL + h));
+            if (g == 4 && h == 1) tc_commit_elect(BAR(B_EFREE));   // every MMA that reads this tile's E operand has been issued
             TRACE(tv == 3, (g * 2 + h) * 3 + 2);
           }
         }
@@ -250,6 +257,78 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
 #ifdef NNB_TC_PROFILE
       if (lane == 0 && blockIdx.x < 148) { for (int i = 0; i < 5; ++i) g_tcprof[blockIdx.x][i] = _pacc[i]; g_tcprof[blockIdx.x][5] = clock64() - _tstart; g_tcprof[blockIdx.x][6] = tv; }
 #endif
+    }
+  } else if (warp >= 10) {
+    // =============================== prologue warps ================================
+    // thread = sample row; one tile ahead of the epilogue warps (E operand double use: released by B_EFREE after layer 4's MMAs)
+    const int row = (warp - 10) * 32 + lane;
+    int tv = -1;
+    for (int tt = 0; tt < my_tiles; ++tt) {
+      const int tile = blockIdx.x + tt * gridDim.x;
+      if (tile >= n_tiles) continue;
+      const int t = ++tv;
+      const size_t m = (size_t)tile * TILE + row;
+      float* rayb = s_rayb + (t & 1) * RAYB_FLOATS;
+      Ray ray; int n, i; float z, p[3];
+      row_geometry_tc(a, m, M, ray, n, i, z, p);
+      float ee[64];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ee[c] = p[c];
+#pragma unroll
+      for (int l = 0; l < 10; ++l) {
+        const float f = (float)(1 << l);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { float sn, cs; sincosf(__fmul_rn(f, p[c]), &sn, &cs); ee[3 + 6 * l + c] = sn; ee[6 + 6 * l + c] = cs; }
+      }
+      ee[63] = 0.f;
+      // direction-encoding term of rgb_layers.0 is constant per ray: fold it into a per-ray bias
+      float v[3], de[32];
+      view_dir(a, ray, v);
+      encode<4>(v, [&](int k, float val) { de[k] = val; });
+#pragma unroll
+      for (int k = 27; k < 32; ++k) de[k] = 0.f;
+      if (stash) {
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4)
+          *reinterpret_cast<float4*>(st.denc + m * 32 + k4 * 4) = make_float4(de[4 * k4], de[4 * k4 + 1], de[4 * k4 + 2], de[4 * k4 + 3]);
+      }
+      // the E operand / this per-ray bias buffer were last read by the tile before the previous one's ... -> wait for B_EFREE
+      mbar_wait(BAR(B_EFREE), ((uint32_t)t & 1u) ^ 1u);
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {
+        const uint4 eh = split_store8_hi(ee + kb * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
+        if (stash && !(st.tcb & 1)) {
+          *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8) = make_float4(ee[kb * 8], ee[kb * 8 + 1], ee[kb * 8 + 2], ee[kb * 8 + 3]);
+          *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8 + 4) = make_float4(ee[kb * 8 + 4], ee[kb * 8 + 5], ee[kb * 8 + 6], ee[kb * 8 + 7]);
+        }
+        if (stash && (st.tcb & 1)) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
+          if (st.wg16) {                 // ... or the fp16 hi half of the E operand itself: [half][kb][64][8], one plane
+            st_stream16(st.xp[0] + (size_t)tile * (PLANE_TILE_64 / 2) + (row >> 6) * 8192 + (row & 63) * 16 + kb * 1024, eh);
+          } else {
+            unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + (row >> 6) * 8192 + (row & 63) * 16;   // [hi|lo][half][kb][64][8]
+            split_stream8_bf16(ee + kb * 8, dst + kb * 1024, dst + 16384 + kb * 1024);
+          }
+        }
+      }
+      const int ray_local = (a.S >= TILE) ? 0 : row / a.S;
+      const bool first_of_ray = (a.S >= TILE) ? (row == 0) : (row % a.S == 0);
+      if (first_of_ray) {   // rows that start a ray publish their direction encoding
+#pragma unroll
+        for (int k = 0; k < 32; ++k) rayb[512 + ray_local * 32 + k] = de[k];
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      {
+        const int nrays = (a.S >= TILE) ? 1 : TILE / a.S;
+        const float* w = a.weights;
+        for (int r = 0; r < nrays; ++r) {
+          float acc = __ldg(w + nnb::B_RGBH + row);
+#pragma unroll
+          for (int k = 0; k < 27; ++k) acc = fmaf(__ldg(w + nnb::W_RGBH + (size_t)row * 283 + 256 + k), rayb[512 + r * 32 + k], acc);
+          rayb[r * 128 + row] = -acc;            // negated like the other biases
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(BAR(B_EREADY));
     }
   } else {
     // =============================== epilogue warps ================================
@@ -271,92 +350,17 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
       const int t = ++tv;        // index among this CTA's valid tiles (barrier phase bookkeeping)
       const size_t m = (size_t)tile * TILE + row;
       PROF_T0();
-      epi_bar();   // previous tile's epilogues are done with s_rayb / s_part
-      // ---- prologue: geometry, positional encoding -> E operand, per-ray direction bias ----
-      Ray ray; int n, i; float z, p[3];
-      row_geometry_tc(a, m, M, ray, n, i, z, p);
-      {
-        // half 0 encodes the raw coordinates + levels 0..4 (E columns 0..32), half 1 levels 5..9 (columns 33..62);
-        // ee[j] holds column 32*half + j.  k-block 4 (columns 32..39) needs column 32 from half 0 -> one exchange.
-        float ee[33];
-        float* s_x = s_part;   // exchange buffer (free until the heads are reduced at the end of the tile)
-        if (half == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) ee[c] = p[c];
-#pragma unroll
-          for (int l = 0; l < 5; ++l) {
-            const float f = (float)(1 << l);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { float sn, cs; sincosf(__fmul_rn(f, p[c]), &sn, &cs); ee[3 + 6 * l + c] = sn; ee[6 + 6 * l + c] = cs; }
-          }
-          s_x[row] = ee[32];
-        } else {
-          ee[31] = 0.f; ee[32] = 0.f;
-#pragma unroll
-          for (int l = 0; l < 5; ++l) {
-            const float f = (float)(32 << l);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { float sn, cs; sincosf(__fmul_rn(f, p[c]), &sn, &cs); ee[1 + 6 * l + c] = sn; ee[4 + 6 * l + c] = cs; }
-          }
-        }
-        epi_bar();
-        if (half == 1) ee[0] = s_x[row];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int kb = half * 4 + kk;
-          const uint4 eh = split_store8_hi(ee + kk * 8, smem + SM_EHI + kb * 2048 + row * 16, smem + SM_ELO + kb * 2048 + row * 16);
-          if (stash && !(st.tcb & 1)) {
-            *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8) = make_float4(ee[kk * 8], ee[kk * 8 + 1], ee[kk * 8 + 2], ee[kk * 8 + 3]);
-            *reinterpret_cast<float4*>(st.enc + m * 64 + kb * 8 + 4) = make_float4(ee[kk * 8 + 4], ee[kk * 8 + 5], ee[kk * 8 + 6], ee[kk * 8 + 7]);
-          }
-          if (stash && (st.tcb & 1)) {   // X plane 0 (encoding) of the weight-gradient pass: bf16 hi|lo, [k/8][row][8]
-            if (st.wg16) {                 // ... or the fp16 hi half of the E operand itself: [half][kb][64][8], one plane
-              st_stream16(st.xp[0] + (size_t)tile * (PLANE_TILE_64 / 2) + (row >> 6) * 8192 + (row & 63) * 16 + kb * 1024, eh);
-            } else {
-              unsigned char* dst = st.xp[0] + (size_t)tile * PLANE_TILE_64 + (row >> 6) * 8192 + (row & 63) * 16;   // [hi|lo][half][kb][64][8]
-              split_stream8_bf16(ee + kk * 8, dst + kb * 1024, dst + 16384 + kb * 1024);
-            }
-          }
-        }
-      }
+      epi_bar();   // previous tile's epilogues are done with s_part
+      const size_t mm_ = m < M ? m : M - 1;
+      const float z = sample_z(a, (int)(mm_ / a.S), (int)(mm_ % a.S));
       const int ray_local = (a.S >= TILE) ? 0 : row / a.S;
-      if (half == 0) {
-        // direction-encoding term of rgb_layers.0 is constant per ray: fold it into a per-ray bias
-        float v[3], de[32];
-        view_dir(a, ray, v);
-        encode<4>(v, [&](int k, float val) { de[k] = val; });
-#pragma unroll
-        for (int k = 27; k < 32; ++k) de[k] = 0.f;
-        if (stash) {
-#pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4)
-            *reinterpret_cast<float4*>(st.denc + m * 32 + k4 * 4) = make_float4(de[4 * k4], de[4 * k4 + 1], de[4 * k4 + 2], de[4 * k4 + 3]);
-        }
-        const bool first_of_ray = (a.S >= TILE) ? (row == 0) : (row % a.S == 0);
-        if (first_of_ray) {   // rows that start a ray publish their direction encoding
-#pragma unroll
-          for (int k = 0; k < 32; ++k) s_rayb[512 + ray_local * 32 + k] = de[k];
-        }
-      }
-      epi_bar();
-      if (half == 1) {
-        const int nrays = (a.S >= TILE) ? 1 : TILE / a.S;
-        const float* w = a.weights;
-        for (int r = 0; r < nrays; ++r) {
-          float acc = __ldg(w + nnb::B_RGBH + row);
-#pragma unroll
-          for (int k = 0; k < 27; ++k) acc = fmaf(__ldg(w + nnb::W_RGBH + (size_t)row * 283 + 256 + k), s_rayb[512 + r * 32 + k], acc);
-          s_rayb[r * 128 + row] = -acc;            // negated like the other biases
-        }
-      }
-      fence_async_smem();
-      mbar_arrive(BAR(B_EREADY));
-      epi_bar();
+      const float* rayb = s_rayb + (t & 1) * RAYB_FLOATS;
+      mbar_wait(BAR(B_EREADY), (uint32_t)t & 1u);     // this tile's per-ray bias (written by the prologue warps) is visible
       float s_logit = 0.f, c_acc[3] = {0.f, 0.f, 0.f};
       PROF_ADD(0);
       // ---- per-GEMM epilogues ----
       for (int g = 0; g < N_GEMM; ++g) {
-        const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : s_rayb + ray_local * 128);
+        const float* bias = (g < 8) ? s_bias + g * 256 : (g == 8 ? s_bias + 2048 : rayb + ray_local * 128);
         const bool planes = stash && (st.tcb & 1);
         const int dbg = st.tcb >> 1;
         const bool wg16 = st.wg16 != 0;
@@ -383,11 +387,17 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
               c_acc[2] = fmaf(v[j], s_bias[2560 + 256 + cb * 32 + j], c_acc[2]);
             }
           }
-          if (stash && (!planes || g == 7 || g == 9)) {
+          if (stash && !(planes && wg16) && (!planes || g == 7 || g == 9)) {     // fp32 side stashes of the heads (exact planes / fp32 backward)
             float* dst = (g < 8) ? st.h[g] + m * 256 : (g == 8 ? st.feat + m * 256 : st.hr + m * 128);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
               __stcs(reinterpret_cast<float4*>(dst + cb * 32 + j4 * 4), make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+          }
+          if (planes && wg16 && g == 9) {   // NNB_WG16: the rgb hidden layer goes out as an fp16 plane too (fc_rgb's weight gradient reads it);
+            unsigned char* hp = reinterpret_cast<unsigned char*>(st.hr) + (size_t)tile * (PLANE_TILE_128 / 2) + (row >> 6) * 16384 + (row & 63) * 16;
+#pragma unroll                                // h7 needs nothing extra: fc_density's weight gradient reads the X plane of fc_feature
+            for (int kb = 0; kb < 4; ++kb)
+              st_stream16(hp + (cb * 4 + kb) * 1024, make_uint4(hw[kb * 4], hw[kb * 4 + 1], hw[kb * 4 + 2], hw[kb * 4 + 3]));
           }
           if (xplane && wg16) {   // the fp16 hi words just written as the next A operand ARE the X plane: 4 x 16 B, no conversion
 #pragma unroll
@@ -417,7 +427,8 @@ __global__ void __launch_bounds__(320, 1) tc_field_fwd(nnb_render_args a, const 
             PROF_ADD(2);
             float v[32];
             uint32_t hw[16], lw[16];
-            const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, hw, lw, true) : epi_chunk32<true>(r, bias + cb * 32, v, hw, lw, g < 9);
+            const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, hw, lw, true)
+                                         : epi_chunk32<true>(r, bias + cb * 32, v, hw, lw, g < 9 || (planes && wg16), g < 9);
             if (g < 9) {
               PROF_ADD(3);
               if (next_tmem) {
@@ -558,9 +569,9 @@ cudaError_t tc_render_fwd(const nnb_render_args& a, const WsLayout& L, cudaStrea
   const int CL = cluster_size_option();
   int grid = n_tiles < n_sm ? n_tiles : n_sm;
   grid = (grid + CL - 1) / CL * CL; if (grid > n_sm) grid = n_sm / CL * CL;
-  if (CL == 4) e = launch_clustered(tc_field_fwd<4>, grid, 320, SM_TOTAL, 4, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
-  else if (CL == 2) e = launch_clustered(tc_field_fwd<2>, grid, 320, SM_TOTAL, 2, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
-  else e = launch_clustered(tc_field_fwd<1>, grid, 320, SM_TOTAL, 1, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
+  if (CL == 4) e = launch_clustered(tc_field_fwd<4>, grid, 448, SM_TOTAL, 4, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
+  else if (CL == 2) e = launch_clustered(tc_field_fwd<2>, grid, 448, SM_TOTAL, 2, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
+  else e = launch_clustered(tc_field_fwd<1>, grid, 448, SM_TOTAL, 1, st, a, (const unsigned char*)img, recs, ts, L.M, n_tiles, stash);
   nnb_prof_mark(st);
   if (e != cudaSuccess) return e;
   e = launch_composite_fwd(a, recs, st);

@@ -963,6 +963,62 @@ __global__ void __launch_bounds__(256) head_wgrad(const float4* __restrict__ dyc
   }
 }
 
+// NNB_WG16 variant: h7 and the rgb hidden layer come from the forward's fp16 planes ([tile][sample half][feature/8][64 samples][8]):
+// one block per tile (strided), threads = (feature block, sample lane): every load is a 16-byte vector, 8 / 16 consecutive samples
+// of one feature block are 128 / 256 contiguous bytes.
+__global__ void __launch_bounds__(256) head_wgrad16(const float4* __restrict__ dyc, const unsigned char* __restrict__ h7p, const unsigned char* __restrict__ hrp,
+                                                     int n_tiles, float* __restrict__ gflat) {
+  const int t = threadIdx.x;
+  const int kbA = t >> 3, slA = t & 7, kbB = t >> 4, slB = t & 15;
+  float aD[8], aC[3][8], ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { aD[j] = 0.f; aC[0][j] = 0.f; aC[1][j] = 0.f; aC[2][j] = 0.f; }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const float4* g4 = dyc + (size_t)tile * 128;
+    const unsigned char* ph = h7p + (size_t)tile * (PLANE_TILE_256 / 2) + kbA * 1024;
+#pragma unroll 4
+    for (int r = slA; r < 128; r += 8) {
+      const float gw = __ldg(&g4[r].w);
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(ph + (r >> 6) * 32768 + (r & 63) * 16));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); aD[2 * i] = fmaf(gw, f.x, aD[2 * i]); aD[2 * i + 1] = fmaf(gw, f.y, aD[2 * i + 1]); }
+    }
+    const unsigned char* pr = hrp + (size_t)tile * (PLANE_TILE_128 / 2) + kbB * 1024;
+#pragma unroll 4
+    for (int r = slB; r < 128; r += 16) {
+      const float4 g = __ldg(&g4[r]);
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(pr + (r >> 6) * 16384 + (r & 63) * 16));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        aC[0][2 * i] = fmaf(g.x, f.x, aC[0][2 * i]); aC[0][2 * i + 1] = fmaf(g.x, f.y, aC[0][2 * i + 1]);
+        aC[1][2 * i] = fmaf(g.y, f.x, aC[1][2 * i]); aC[1][2 * i + 1] = fmaf(g.y, f.y, aC[1][2 * i + 1]);
+        aC[2][2 * i] = fmaf(g.z, f.x, aC[2][2 * i]); aC[2][2 * i + 1] = fmaf(g.z, f.y, aC[2][2 * i + 1]);
+      }
+    }
+    if (t < 128) { const float4 g = __ldg(&g4[t]); ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = aD[j];
+    x += __shfl_xor_sync(0xffffffffu, x, 1); x += __shfl_xor_sync(0xffffffffu, x, 2); x += __shfl_xor_sync(0xffffffffu, x, 4);
+    if (slA == 0) atomicAdd(gflat + nnb::W_SIG + kbA * 8 + j, x);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float y = aC[c][j];
+      y += __shfl_xor_sync(0xffffffffu, y, 1); y += __shfl_xor_sync(0xffffffffu, y, 2); y += __shfl_xor_sync(0xffffffffu, y, 4); y += __shfl_xor_sync(0xffffffffu, y, 8);
+      if (slB == 0) atomicAdd(gflat + nnb::W_RGB + c * 128 + kbB * 8 + j, y);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float s = warp_sum(ab[c]);
+    if ((t & 31) == 0 && t < 128) atomicAdd(gflat + (c < 3 ? nnb::B_RGB + c : nnb::B_SIG), s);
+  }
+}
+
 bool g_table_t_ready = false;
 cudaError_t upload_stage_table_t() {
   if (g_table_t_ready) return cudaSuccess;
@@ -1115,7 +1171,10 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
     if (e != cudaSuccess) return e;
     {  // small heads: fc_density / fc_rgb (streaming reduction); the direction slice of rgb_layers.0 rides on ray_dir_grad
       const int chunk = 256;
-      head_wgrad<<<(unsigned)((L.M + chunk - 1) / chunk), 256, 0, sx>>>(reinterpret_cast<const float4*>(base + L.dyc),
+      if (wg16) head_wgrad16<<<n_tiles < n_sm ? n_tiles : n_sm, 256, 0, sx>>>(reinterpret_cast<const float4*>(base + L.dyc),
+                                                                               reinterpret_cast<const unsigned char*>(base + L.xp[8]),
+                                                                               reinterpret_cast<const unsigned char*>(base + L.hr), n_tiles, b.g_weights);
+      else head_wgrad<<<(unsigned)((L.M + chunk - 1) / chunk), 256, 0, sx>>>(reinterpret_cast<const float4*>(base + L.dyc),
                                                                          reinterpret_cast<const float*>(base + L.h[7]),
                                                                          reinterpret_cast<const float*>(base + L.hr), L.M, chunk, b.g_weights);
       e = cudaGetLastError();

@@ -115,7 +115,8 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
 //                                 to tensor memory (row = lane, two k per column) -- and, with NNB_WG16, hw[] IS the X plane of the
 //                                 weight-gradient pass
 template <bool RELU>
-__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* nbias, float* v, uint32_t* hw, uint32_t* lw, bool want_words) {
+__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* nbias, float* v, uint32_t* hw, uint32_t* lw, bool want_words,
+                                                bool want_lo = true) {
   uint32_t mw = 0;
   const ulonglong2* nb = reinterpret_cast<const ulonglong2*>(nbias);
 #pragma unroll
@@ -132,10 +133,13 @@ __device__ __forceinline__ uint32_t epi_chunk32(const uint32_t* r, const float* 
       } else { v[j] = -n0; v[j + 1] = -n1; }
       if (want_words) {
         __half2 hh = __floats2half2_rn(v[j], v[j + 1]);
-        const float2 hf = __half22float2(hh);
-        float l0, l1; f2_unpack(f2_sub(f2_pack(v[j], v[j + 1]), f2_pack(hf.x, hf.y)), l0, l1);
-        __half2 ll = __floats2half2_rn(l0, l1);
-        hw[j >> 1] = *reinterpret_cast<uint32_t*>(&hh); lw[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+        hw[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        if (want_lo) {
+          const float2 hf = __half22float2(hh);
+          float l0, l1; f2_unpack(f2_sub(f2_pack(v[j], v[j + 1]), f2_pack(hf.x, hf.y)), l0, l1);
+          __half2 ll = __floats2half2_rn(l0, l1);
+          lw[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+        }
       }
     }
   }

@@ -94,9 +94,12 @@ def oracle32(g):
 
 
 @pytest.mark.parametrize("name", RENDER_CASES)
-@pytest.mark.parametrize("eng", ["simt", "tc"])
-def test_render_vs_reference_golden(name, eng):
-    """Outputs: <= 1e-4 of the reference.  Gradients, two kinds of case:
+@pytest.mark.parametrize("eng,wg", [("simt", "exact"), ("tc", "exact"), ("tc", "fp16")])
+def test_render_vs_reference_golden(name, eng, wg, monkeypatch):
+    """wg = weight-gradient operand planes of the tcgen05 backward ('fp16' = NNB_WG16, the default: the MLP parameter digests then carry
+    fp16 operand rounding, gate 2e-3 at these sample counts of 768 .. 6144 -- measured up to 7.3e-4 on the 3 x 128 / 1 x 256 head
+    matrices; outputs and every pose / distortion / intrinsics gradient keep the gates below in both modes).
+    Outputs: <= 1e-4 of the reference.  Gradients, two kinds of case:
       * `*_damped` (oracle.init_params(hf_damp=True): no ReLU-gate switches between fp32 evaluation orders): every gradient
         <= 1e-4 of the fp64 truth (MLP parameter digests 5e-4) and <= max(1e-4, 3 x the reference's own distance from it);
       * default-initialised cases: gradients carry gate-switch noise (tests/test_oracle_golden.py::test_render_gate_matched_and_kxy):
@@ -105,6 +108,8 @@ def test_render_vs_reference_golden(name, eng):
     engine = dict(engines()).get(eng)
     if engine is None:
         pytest.skip("engine disabled")
+    from nope_nerf_b200 import ops as _ops
+    monkeypatch.setattr(_ops, "_WGRAD", [wg])
     g = load_golden(name)
     damped = bool(g.get("hf_damp", False))
     out, grads = run_case_cuda(g, engine)
@@ -125,7 +130,7 @@ def test_render_vs_reference_golden(name, eng):
     for k, (ours, ref, t64, t32) in terms.items():
         e["g_" + k] = relmax(ours, ref); e["g_%s_vs64" % k] = relmax(ours, t64); e["g_%s_vs32" % k] = relmax(ours, t32)
         e["env_" + k] = max(relmax(t64, ref), relmax(t32, t64)); e["ref64_" + k] = relmax(t64, ref)
-    _report("%s/%s" % (name, eng), **e)
+    _report("%s/%s%s" % (name, eng, "" if wg == "exact" else "-wg16"), **e)
     tol = 1e-4
     for k in ("rgb", "depth_pred", "depth_gt", "z", "c2w"):
         assert e[k] < tol, (k, e[k])
@@ -140,7 +145,7 @@ def test_render_vs_reference_golden(name, eng):
             assert e["g_" + k] < max(1e-4, 3 * e["ref64_" + k]), (k, e)
         else:
             assert e["g_" + k] < max(flip_floor, 3 * e["env_" + k]), (k, e)
-    assert e["g_params"] < max(5e-4, 3 * e["env_params"], flip_floor if not damped else 0.0), e
+    assert e["g_params"] < max(2e-3 if wg == "fp16" else 5e-4, 3 * e["env_params"], flip_floor if not damped else 0.0), e
 
 
 def test_pose_expmap_kernels():
@@ -664,10 +669,12 @@ def test_native_ref_stage_vs_oracle(name):
 
 
 @pytest.mark.parametrize("N,S", [(5, 32), (3, 64), (7, 32), (130, 32), (33, 64), (999, 128), (9, 256)])
-def test_ragged_last_tile_tc_vs_simt(N, S):
+def test_ragged_last_tile_tc_vs_simt(N, S, monkeypatch):
     """N*S not a multiple of the 128-sample tile: the tcgen05 engine pads the last tile with clamped rows whose cotangents are
     zero; outputs and gradients must agree with the exact-fp32 engine (weights from init_params(hf_damp=True), so that the
     comparison of the two engines' GRADIENTS is not dominated by single ReLU-gate switches on a handful of rays)."""
+    from nope_nerf_b200 import ops as _ops_
+    monkeypatch.setattr(_ops_, "_WGRAD", ["exact"])       # tiling test: exact weight-gradient planes so that TC == SIMT to 5e-4
     from nope_nerf_b200 import ops, _lib as L
     if len(engines()) < 2:
         pytest.skip("needs both engines")
