@@ -172,6 +172,7 @@ def run_ours(args):
         dist.barrier()
     from nope_nerf_b200 import ops, _lib as L
     ops.set_default_engine(args.engine)
+    WG_DEFAULT = ops.wgrad_precision()
     weak = args.scaling == "weak"
     n_local = NRAYS if weak else NRAYS // world
     trainer = build_trainer(make_cfg(n_local * world), dev, V)
@@ -255,8 +256,27 @@ def run_ours(args):
         extra["strong"] = {"value": round(NRAYS * S * 300 / (ms_s / 1e3), 1), "unit": "ray-samples/s", "ms_per_step": round(ms_s / 300, 4),
                            "global_rays": NRAYS, "rays_per_gpu": NRAYS // world, "steps": 300}
         del tr_s
+    if world > 1 and weak:
+        # C5 (BASELINE.json configs[4]): 4096 rays x 128 samples over the GPUs, one view per rank, full default loss set, one exchange
+        ops_c5 = make_cfg(4096 // world, full_loss=True)
+        tr_c = build_trainer(ops_c5, dev, V, dp_mode="views")
+        hostf, devf = synth_frames(H, W, HD, WD, 2 * world, V, dev, with_ref=True)
+        mine = [devf[(2 * k + rank) % len(devf)] for k in range(2)]
+        ms_c, ldc = timed(tr_c, mine, 200, 5, sync_loss=False)
+        extra["c5"] = {"value": round(4096 * S * 200 / (ms_c / 1e3), 1), "unit": "ray-samples/s", "ms_per_step": round(ms_c / 200, 4), "global_rays": 4096,
+                       "rays_per_gpu": 4096 // world, "steps": 200,
+                       "workload": "C5: 4096 rays x 128 samples, dp_mode='views' (one view per rank), rgb + depth + point-cloud + warped-RGB losses"}
+        del tr_c, hostf, devf
     if world == 1:
         extra.update(single_gpu_records(dev, step, timed, args))
+        # the same step with the exact (bf16 hi|lo, three MMAs per product) weight-gradient planes
+        ops.set_wgrad_precision("exact")
+        tr_x = build_trainer(make_cfg(NRAYS), dev, V)
+        ms_x, _ = timed(tr_x, devd, 300, 5, sync_loss=False)
+        ops.set_wgrad_precision(WG_DEFAULT)
+        extra["exact_wgrad_planes"] = {"ms_per_step": round(ms_x / 300, 4), "value": round(NRAYS * S * 300 / (ms_x / 1e3), 1), "steps": 300,
+                                       "note": "NNB_WGRAD=exact: MLP weight gradients to fp32 round-off (bf16 hi|lo planes) instead of fp16 operand rounding"}
+        del tr_x
     if rank == 0:
         pk = peaks()
         samples_per_step = n_local * world * S
@@ -279,11 +299,13 @@ def run_ours(args):
                     "note": "algorithmic fp32-equivalent FLOPs; the tcgen05 engine issues split 16-bit MMAs per logical product"}
         line = {"metric": "train-step ray-samples/sec", "value": round(value, 1), "unit": "ray-samples/s", "n_gpus": world, "steps": K,
                 "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
-                "dtype": "fp32 (split 16-bit tcgen05 MMAs, fp32 accumulate)" if args.engine == "tc" else "fp32", "data": "synthetic",
+                "dtype": ("fp32 (forward / data gradients: split fp16|bf16 hi+lo tcgen05 MMAs, fp32 accumulate; weight gradients: %s)" %
+                          ("one fp16 plane per operand, NNB_WG16" if ops.wgrad_precision() == "fp16" else "bf16 hi+lo planes")) if args.engine == "tc" else "fp32",
+                "data": "synthetic",
                 "config": {"workload": "C2 Ignatius-shape 1080x1920, V=200, 1024 rays x 128 samples, uniform+jitter, rgb L1 + depth L1, Adam x3",
                            "global_rays": n_local * world, "rays_per_gpu": n_local, "samples_per_ray": S,
                            "parallelism": "dp%d (ray shards, 1 all-reduce)" % world,
-                           "engine": args.engine, "frames_resident": N_FRAMES, "cuda_graph": bool(trainer.use_cuda_graph),
+                           "engine": args.engine, "wgrad_planes": ops.wgrad_precision(), "frames_resident": N_FRAMES, "cuda_graph": bool(trainer.use_cuda_graph),
                            "l2_policy": "no flush: each step streams a >1 GB activation stash, far larger than the 126 MB L2",
                            "settle": "W warm-up steps + ~1 s of untimed steps before the K timed steps"},
                 "sustained": {"steps": 1000, "ms_per_step": round(ms_sus / 1000, 4), "value": round(samples_per_step * 1000 / (ms_sus / 1e3), 1)},
