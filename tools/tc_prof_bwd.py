@@ -6,10 +6,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ["NNB_CUDA_GRAPH"] = "0"
+import torch
 import bench
 from nope_nerf_b200 import _lib as L
-a = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", engine="tc", no_cpu_baseline=True, scaling="weak")
-bench.run_ours(a)
+dev = torch.device("cuda", 0); torch.cuda.set_device(0)
+tr = bench.build_trainer(bench.make_cfg(bench.NRAYS), dev, bench.V)
+_, devd = bench.synth_frames(bench.H, bench.W, bench.HD, bench.WD, 2, bench.V, dev, with_ref=False)
+for i in range(8):
+    tr.train_step(devd[i % 2], it=i, epoch=0, scheduling_start=10000, render_path=None)
+torch.cuda.synchronize()
 buf = (C.c_ulonglong * (148 * 16))()
 L.lib.nnb_debug_dgprof(buf)
 d = np.array(buf[:], dtype=np.float64).reshape(148, 16)
