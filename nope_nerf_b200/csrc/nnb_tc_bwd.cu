@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
                 const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
                 if (lane == 0) atomicMax(&s_amax[di], mb);
               }
-              if (write_dy) {   // bias gradient of this layer: db[n] = sum_m dY[m][n] (off the MMA's critical path)
+              if (write_dy && !wg16) {   // bias gradient of this layer: db[n] = sum_m dY[m][n] (NNB_WG16: tc_wgrad16 takes the column sums)
                 const float cs = warp_colsum32(v, lane);
                 atomicAdd(&s_colsum[di * 256 + cb * 32 + lane], cs * inv_gscale);
               }
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   tc_fence_before();
   __syncthreads();
   if (wg16 && threadIdx.x < 10 && s_amax[threadIdx.x]) atomicMax(reinterpret_cast<unsigned int*>(P.wg_state) + 16 + threadIdx.x, s_amax[threadIdx.x]);
-  if (write_dy && P.g_weights) {   // flush this CTA's bias-gradient partial sums
+  if (write_dy && P.g_weights && !wg16) {   // flush this CTA's bias-gradient partial sums
     for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) {
       const int di = i >> 8, n = i & 255;
       atomicAdd(P.g_weights + (di < 8 ? nnb::b_off(di) : nnb::B_FEAT) + n, s_colsum[i]);
@@ -482,6 +482,7 @@ struct WgJob {
   int paired;                                        // 1: the two CTAs of a pair take the two 128-row halves of dW; 0: they split the tiles
   int cost;                                          // bytes-per-tile weight used to balance the CTA pairs
   int dyi;                                           // index of the dY plane (per-layer scale of the NNB_WG16 planes)
+  int b_off;                                         // NNB_WG16: float offset of this layer's bias gradient (column sums of dY), or -1
 };
 constexpr int MAX_WG_JOBS = 12;
 struct WgJobs { WgJob j[MAX_WG_JOBS]; int njobs, n_tiles, x_lo; const float* wg_state; };   // x_lo = 0: activation planes carry the bf16 hi half only
@@ -707,11 +708,14 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad(WgJobs jobs, float* __restric
 // ---------------------------------------------------------------------------------------------------
 // NNB_WG16 weight gradients: ONE fp16 plane per operand (X = hi half of the forward's operands, dY = fp16 of dY * 2^k),
 // one MMA per K-step.  48 KB per 64-sample half-tile (dY 16 KB | X 32 KB) streamed through a 4-deep ring: the kernel is a pure
-// HBM stream (1.34 GB at 1024 x 128), the tensor pipe idles ~3/4 of the time.  Accumulation / flush as in tc_wgrad; the flush
-// multiplies by 2^-k of the job's dY plane.
+// HBM stream (1.34 GB at 1024 x 128), the tensor pipe idles ~3/4 of the time -- so the BIAS gradients ride along: one more N = 16 MMA
+// per K-step against a tile of ones accumulates the column sums of dY in 16 spare TMEM columns (the data-gradient kernel's epilogue,
+// the serial resource of the backward, no longer spends 30 % of its instructions on shuffle reductions).  One accumulation group per
+// segment (<= 8 MMAs per tile: the truncation of the tensor core's fp32 adds stays below 2e-5); the flush multiplies by 2^-k.
 // ---------------------------------------------------------------------------------------------------
 constexpr int W16_SET = 49152, W16_NSET = 4, W16_A = 0, W16_B = 16384;
-constexpr int W16_XPOSE = W16_NSET * W16_SET;
+constexpr int W16_ONES = W16_NSET * W16_SET;        // 16 features x 64 samples of fp16 ones (MN-major): B operand of the bias-gradient MMAs
+constexpr int W16_XPOSE = W16_ONES + 2048;
 constexpr int W16_SEG = W16_XPOSE + 4 * 32 * 17 * 4;
 constexpr int W16_BAR = W16_SEG + 16 * 16;
 constexpr int W16_TOTAL = W16_BAR + 16 * 8 + 16;
@@ -752,6 +756,8 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad16(WgJobs jobs, float* __restr
     s_nseg = ns;
   }
   if (threadIdx.x >= 32 && threadIdx.x < 42) { const float sc = jobs.wg_state[threadIdx.x - 32]; s_inv[threadIdx.x - 32] = sc > 0.f ? 1.f / sc : 1.f; }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + W16_ONES)[i] = 0x3c003c00u;   // fp16 1.0 pairs
+  fence_async_smem();
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -786,28 +792,37 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad16(WgJobs jobs, float* __restr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // converged MMA warp (elect.sync lane issues), MN-major descriptors from precomputed low words: LBO = 128 B, SBO = 1024 B
+      constexpr uint32_t DHI_MN = 64u | (1u << 14);
+      const uint32_t set0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (8u << 16);
+      const uint32_t ones = ((smem_u32(smem + W16_ONES) >> 4) & 0x3FFFu) | (8u << 16);
       uint32_t it = 0, gcount = 0;
       for (int si = 0; si < nseg; ++si) {
         const WgSeg sg = segs[si];
         const WgJob& J = jobs.j[sg.job];
         const uint32_t idesc = make_idesc_ex(128, J.N, 0, 0, 1, 1);     // fp16 x fp16, both MN-major
+        const uint32_t idesc_b = make_idesc_ex(128, 16, 0, 0, 1, 1);
+        const bool bias = J.b_off >= 0;
         uint32_t acc = 0;
         for (int t = sg.t0; t < sg.t1; ++t) {
           if (acc == 0 && gcount > 0) { mbar_wait(BAR(H_DRAINED), (gcount - 1) & 1u); tc_fence_after(); }
 #pragma unroll
           for (int h = 0; h < 2; ++h, ++it) {
             const int set = it % W16_NSET;
-            const uint32_t ph = (it / W16_NSET) & 1u, sb = smem_u32(smem + set * W16_SET);
+            const uint32_t ph = (it / W16_NSET) & 1u;
+            const uint32_t sa = set0 + set * (W16_SET >> 4), sbb = sa + (W16_B >> 4);
             mbar_wait(BAR(H_FULL + set), ph);
             tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              tc_mma_f16(tmem_base, make_desc(sb + W16_A + ks * 256, 128, 1024), make_desc(sb + W16_B + ks * 256, 128, 1024), idesc, acc | (uint32_t)(ks > 0));
+            for (int ks = 0; ks < 4; ++ks) tc_mma_lo_elect(tmem_base, sa + ks * 16, sbb + ks * 16, DHI_MN, idesc, acc | (uint32_t)(ks > 0));
+            if (bias) {   // column sums of this dY half-tile: dY^T (128 features x 64 samples) times ones (64 samples x 16)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) tc_mma_lo_elect(tmem_base + 256, sa + ks * 16, ones + ks * 16, DHI_MN, idesc_b, acc | (uint32_t)(ks > 0));
+            }
             acc = 1u;
-            tc_commit(BAR(H_EMPTY + set));
+            tc_commit_elect(BAR(H_EMPTY + set));
           }
-          if (((t - sg.t0 + 1) % WG_GROUP) == 0 || t + 1 == sg.t1) { tc_commit(BAR(H_DONE)); ++gcount; acc = 0; }
+          if (t + 1 == sg.t1) { tc_commit_elect(BAR(H_DONE)); ++gcount; acc = 0; }
         }
       }
     }
@@ -822,39 +837,33 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad16(WgJobs jobs, float* __restr
       const float inv = s_inv[J.dyi];
       const int n_base = (J.paired && J.dy_feat == 256) ? side * 128 : 0;
       float* dst0 = gflat + J.w_off + (size_t)(n_base + q * 32) * J.ldw;
-      const int ngroups = (sg.t1 - sg.t0 + WG_GROUP - 1) / WG_GROUP, nchunks = J.N / 32;
-      for (int gi = 0; gi < ngroups; ++gi, ++gcount) {
-        mbar_wait(BAR(H_DONE), gcount & 1u);
+      const int nchunks = J.N / 32;
+      {
+        mbar_wait(BAR(H_DONE), gcount & 1u); ++gcount;
         tc_fence_after();
-        const bool last = (gi + 1 == ngroups);
         for (int cb = 0; cb < nchunks; ++cb) {
           uint32_t r[32];
           tc_ld32(lane_addr + cb * 32, r);
-          if (gi > 0) {
-            uint32_t r2[32];
-            tc_ld32(lane_addr + 256 + cb * 32, r2);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-          }
-          if (!last) {
-            tc_st32(lane_addr + 256 + cb * 32, r);
-          } else {
+          for (int hc = 0; hc < 2; ++hc) {
 #pragma unroll
-            for (int hc = 0; hc < 2; ++hc) {
+            for (int j = 0; j < 16; ++j) xp[lane * 17 + j] = __uint_as_float(r[hc * 16 + j]) * inv;
+            __syncwarp();
+            const int k = cb * 32 + hc * 16 + (lane & 15);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) xp[lane * 17 + j] = __uint_as_float(r[hc * 16 + j]) * inv;
-              __syncwarp();
-              const int k = cb * 32 + hc * 16 + (lane & 15);
-#pragma unroll
-              for (int rr = 0; rr < 32; rr += 2) {
-                const int rw = rr + (lane >> 4);
-                if (k < J.kvalid) atomicAdd(dst0 + (size_t)rw * J.ldw + k, xp[rw * 17 + (lane & 15)]);
-              }
-              __syncwarp();
+            for (int rr = 0; rr < 32; rr += 2) {
+              const int rw = rr + (lane >> 4);
+              if (k < J.kvalid) atomicAdd(dst0 + (size_t)rw * J.ldw + k, xp[rw * 17 + (lane & 15)]);
             }
+            __syncwarp();
           }
         }
-        if (!last) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (J.b_off >= 0) {   // bias gradient: every one of the 16 columns holds sum_m dY[m][feature of this lane]
+          uint32_t rb[4];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rb[0]), "=r"(rb[1]), "=r"(rb[2]), "=r"(rb[3]) : "r"(lane_addr + 256));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          atomicAdd(gflat + J.b_off + n_base + q * 32 + lane, __uint_as_float(rb[0]) * inv);
+        }
         tc_fence_before();
         mbar_arrive(BAR(H_DRAINED));
       }
@@ -1154,6 +1163,7 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
       j.x = reinterpret_cast<const unsigned char*>(base + L.xp[xi]);
       j.x_tile = (N == 256 ? (int)PLANE_TILE_256 : (int)PLANE_TILE_64) / pdiv;
       j.N = N; j.ldw = ldw; j.kvalid = kvalid; j.w_off = w_off; j.paired = paired; j.cost = wg16 ? (N == 256 ? 48 : 24) * (paired ? 2 : 1) / 2 : cost; j.dyi = dyi;
+      j.b_off = -1;
     };
     // cost = measured MMA-thread cycles per tile and CTA pair (N = 256 tiles are DRAM-bound, N = 64 tiles issue-bound), /80
     add(0, 256, 0, 64, nnb::w_off(0), 63, 63, 1, 40);                                        // layer 0: X = enc (biases: tc_dgrad / ray_dir_grad)
@@ -1161,6 +1171,11 @@ cudaError_t tc_render_bwd_planes(const nnb_render_bwd_args& b, const WsLayout& L
     add(4, 256, 0, 64, nnb::w_off(4) + 256, 319, 63, 1, 40);                                 // layer 4 enc slice
     add(8, 256, 8, 256, nnb::W_FEAT, 256, 256, 1, 54);                                       // fc_feature: X = h7 = xp[8]
     add(9, 128, 9, 256, nnb::W_RGBH, 283, 256, 0, 27);                                       // rgb_layers.0[:, :256]: X = feat; the pair splits the tiles
+    if (wg16) {   // bias gradients = column sums of the dY planes, taken by the jobs that stream those planes anyway (layer 4 once)
+      J.j[0].b_off = nnb::b_off(0);
+      for (int l = 1; l < 8; ++l) J.j[l].b_off = nnb::b_off(l);
+      J.j[9].b_off = nnb::B_FEAT;
+    }
     J.njobs = nj; J.n_tiles = n_tiles;
     { static const int xlo = [] { const char* v = getenv("NNB_DBG_FWD"); return (v && (atoi(v) & 4)) ? 0 : 1; }(); J.x_lo = xlo; }
     const int grid_w = n_sm >= 2 ? (n_sm / 2) * 2 : 2;

@@ -194,9 +194,14 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
   uint32_t d; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d;
 }
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ void stream8_f16_scaled(const float* v, float scale, unsigned char* dst) {
-  st_stream16(dst, make_uint4(pack_half2_sat(v[0] * scale, v[1] * scale), pack_half2_sat(v[2] * scale, v[3] * scale),
-                              pack_half2_sat(v[4] * scale, v[5] * scale), pack_half2_sat(v[6] * scale, v[7] * scale)));
+  const unsigned long long s2 = f2_pack(scale, scale);
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float a, b; f2_unpack(f2_mul(f2_pack(v[2 * i], v[2 * i + 1]), s2), a, b); w[i] = pack_half2_sat(a, b); }   // packed FMUL2
+  st_stream16(dst, make_uint4(w[0], w[1], w[2], w[3]));
 }
 // bf16 hi (and optionally lo) operand plane of 8 values, streamed to global memory
 __device__ __forceinline__ void plane_stream8_bf16(const float* v, unsigned char* hi_dst, unsigned char* lo_dst, bool with_lo) {
@@ -489,6 +494,16 @@ __device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint
         : "memory");
   }
   return ok;
+}
+// single MMA from descriptor LOW words (high word shared), issued by the elect.sync lane of a converged warp
+__device__ __forceinline__ void tc_mma_lo_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %3};\n\t mov.b64 db, {%2, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 }  // namespace tcu
