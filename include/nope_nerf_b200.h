@@ -33,6 +33,8 @@ extern "C" {
 #define NNB_SHIFT_FIRST 128u /* training.shift_first    (training.py:241-245)                     */
 #define NNB_STASH 256u      /* keep activations in the workspace for nnb_render_bwd               */
 #define NNB_TCBWD 512u      /* NNB_ENGINE_TC only: tcgen05 backward (operand-image stash) instead of the fp32 one */
+#define NNB_RAW_DENSITY 2048u /* nnb_field_fwd/bwd only: out_rgba[3] = the density LOGIT (fc_density output, official_nerf.py:66-67
+                                * infer_occ) instead of alpha / sigma; used for OfficialStaticNerf.gradient() (normals)            */
 #define NNB_WG16 1024u      /* with NNB_TCBWD: the weight-gradient GEMMs dW = dY^T X read ONE fp16 plane per operand (X = the hi
                              * half of the forward's fp16 hi|lo operand, dY = fp16 of dY * 2^k with a per-layer power-of-two scale
                              * taken from the previous step's max |dY|, "delayed scaling") instead of bf16 hi|lo planes: half the

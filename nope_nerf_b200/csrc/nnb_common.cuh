@@ -170,12 +170,14 @@ __device__ __forceinline__ float softplus_f(float s) { return s > 20.f ? s : log
 __device__ __forceinline__ float sigmoid_f(float s) { return 1.f / (1.f + expf(-s)); }
 // density logit -> MLP output a (alpha if !dist_alpha else sigma) (official_nerf.py:77-83)
 __device__ __forceinline__ float density_act(float s, uint32_t flags, float* sigma_out) {
+  if (flags & NNB_RAW_DENSITY) { *sigma_out = s; return s; }      // explicit-point queries for infer_occ / gradient(): the logit itself
   float sigma = (flags & NNB_SOFTPLUS) ? softplus_f(s) : fmaxf(s, 0.f);
   *sigma_out = sigma;
   return (flags & NNB_DIST_ALPHA) ? sigma : 1.f - expf(-sigma);
 }
 // d a / d s
 __device__ __forceinline__ float density_act_grad(float s, uint32_t flags) {
+  if (flags & NNB_RAW_DENSITY) return 1.f;
   float sigma = (flags & NNB_SOFTPLUS) ? softplus_f(s) : fmaxf(s, 0.f);
   float ds = (flags & NNB_SOFTPLUS) ? (s > 20.f ? 1.f : sigmoid_f(s)) : (s > 0.f ? 1.f : 0.f);
   return (flags & NNB_DIST_ALPHA) ? ds : expf(-sigma) * ds;

@@ -41,11 +41,12 @@ class _FieldFn(torch.autograd.Function):
         return (None, None, g_p[:, :3], g_d[:, :3] if ctx.has_d else None) + tuple(gp)
 
 
-def field_query(net, p, ray_d):
-    """returns (rgb (..,3), a (..,1)) with a = alpha (or sigma when rendering.dist_alpha), like return_addocc=True"""
+def field_query(net, p, ray_d, raw_density=False):
+    """returns (rgb (..,3), a (..,1)) with a = alpha (or sigma when rendering.dist_alpha), like return_addocc=True;
+    raw_density: a = the density logit (OfficialStaticNerf.infer_occ, official_nerf.py:60-67)"""
     ops._need_cuda(p, "p")
     shp = p.shape[:-1]
-    flags = (L.DIST_ALPHA if net.dist_alpha else 0) | (L.SOFTPLUS if net.occ_activation == 'softplus' else 0)
+    flags = (L.DIST_ALPHA if net.dist_alpha else 0) | (L.SOFTPLUS if net.occ_activation == 'softplus' else 0) | (L.RAW_DENSITY if raw_density else 0)
     d = None if ray_d is None else ray_d.reshape(-1, 3)
     rgb, a = _FieldFn.apply(flags, net.flat_weights(), p.reshape(-1, 3), d, *list(net.parameters()))
     return rgb.reshape(*shp, 3), a.reshape(*shp, 1)

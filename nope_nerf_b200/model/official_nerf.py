@@ -91,10 +91,21 @@ class OfficialStaticNerf(nn.Module):
 
     # ---- reference API -------------------------------------------------------------------
     def infer_occ(self, p):
-        raise NotImplementedError("infer_occ is only used by the phong/normal path (SURVEY.md 8(f) rank 4)")
+        """official_nerf.py:60-67: (trunk features, density logit).  The trunk features never leave the kernel here; callers in the
+        reference (gradient(), forward()) only use the logit, so the first element is None."""
+        from ..field import field_query
+        _, s = field_query(self, p, None, raw_density=True)
+        return None, s
 
     def gradient(self, p, it):
-        raise NotImplementedError("gradient() (normals) is outside the hot path (SURVEY.md 8(f) rank 4)")
+        """official_nerf.py:46-58: -d(density logit)/d p, shape (N, 1, 3) (surface normals of the geometry view).  The reference
+        differentiates infer_occ with autograd; here it is the data-gradient chain of the field kernel with cotangent 1 on the logit."""
+        from ..field import field_query
+        with torch.enable_grad():
+            q = p.detach().clone().requires_grad_(True)
+            _, s = field_query(self, q, None, raw_density=True)
+            g, = torch.autograd.grad(s, q, torch.ones_like(s), create_graph=False, retain_graph=False, allow_unused=True)
+        return -g.unsqueeze(1)
 
     def forward(self, p, ray_d=None, only_occupancy=False, return_logits=False, return_addocc=False,
                 noise=False, it=100000, **kwargs):

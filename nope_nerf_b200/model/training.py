@@ -469,8 +469,9 @@ class Trainer(object):
         self.weight_dist_2nd_loss = cfg['weight_dist_2nd_loss']
         self.weight_dist_1st_loss = cfg['weight_dist_1st_loss']
         self.depth_consistency_weight = cfg['depth_consistency_weight']
-        if cfg['depth_loss_type'] != 'l1':
-            raise NotImplementedError("depth_loss_type='invariant' is not fused (default is 'l1', configs/default.yaml:102)")
+        if cfg['depth_loss_type'] not in ('l1', 'invariant'):
+            raise ValueError("training.depth_loss_type must be 'l1' or 'invariant' (losses.py:59-64)")
+        self.depth_loss_type = cfg['depth_loss_type']     # 'invariant' (median / mean-abs-deviation normalised, losses.py:34-57) takes the general path
         self.loss = Loss(cfg)
         # ---- data parallel (new component) ----
         self.dp_group = kwargs.get('process_group', None)
@@ -593,6 +594,8 @@ class Trainer(object):
         """fast path: the whole step as one fixed kernel sequence / CUDA graph.  Returns (graph step, device weights) or None for
         configurations that take the general path (learnable focal, pose-smoothness terms, no render terms, foreign optimizers)."""
         if not self.fused_adam or self.optimizer_focal or self.pose_param_net is None or self.distortion_net is None:
+            return None
+        if self.depth_loss_type != 'l1':
             return None
         if self.optimizer_pose is None or self.optimizer_distortion is None:
             return None
@@ -770,9 +773,20 @@ class Trainer(object):
                                   near=0.0 if ndc else rend.depth_range[0], far=1.0 if ndc else rend.depth_range[1],
                                   ray_idx=ray_idx, depth_map=depth_input.detach().reshape(h_depth, w_depth).contiguous(),
                                   scale=scale_dev, shift=shift_dev, noise=noise, H=h, W=w, stash=backward)
+            inv = self.depth_loss_type == 'invariant' and weights['depth_weight'] != 0.0
             out4, g_rgb, g_dp, g_dg = ops.loss_rgb_depth(call.rgb, call.depth_pred, call.depth_gt, call.mask,
-                                                         weights['rgb_weight'], weights['depth_weight'], rgb_loss_type == 'l2',
+                                                         weights['rgb_weight'], 0.0 if inv else weights['depth_weight'], rgb_loss_type == 'l2',
                                                          img=img.reshape(3, h * w), ray_idx=ray_idx, grad_scale=grad_scale)
+            if inv:
+                # scale / shift invariant depth term (losses.py:34-57, off by default): a median and two mean-abs-deviations over the
+                # N masked rays -- N-element glue, the seeds it yields go through the same fused backward as the L1 seeds
+                m = call.mask.bool()
+                dpv = call.depth_pred.detach()[m].requires_grad_(True); dgv = call.depth_gt.detach()[m].requires_grad_(True)
+                l_inv = self.loss.depth_loss_dpt(dpv, dgv)
+                gp_, gg_ = torch.autograd.grad(l_inv * (weights['depth_weight'] * grad_scale), [dpv, dgv])
+                g_dp = g_dp.clone(); g_dg = g_dg.clone()
+                g_dp[m] += gp_; g_dg[m] += gg_
+                out4 = out4.clone(); out4[0] += weights['depth_weight'] * l_inv.detach(); out4[2] = l_inv.detach()
             losses4 += out4 * grad_scale if self.world > 1 else out4
             if backward:
                 g_c2w = torch.zeros(4, 4, device=device)
@@ -864,7 +878,7 @@ class Trainer(object):
 
     # ------------------------------------------------------------------------------------
     def render_visdata(self, data, resolution, it, out_render_path):
-        """training.py:100-163 (nope_nerf render only; the phong geometry view is out of scope)."""
+        """training.py:100-163: the volumetric view and, with training.vis_geo, the phong-shaded geometry view."""
         (img, dpt, camera_mat, scale_mat, img_idx) = self.process_data_dict(data)
         h, w = resolution
         c2w = self.pose_param_net(int(img_idx)).detach()
@@ -886,4 +900,12 @@ class Trainer(object):
             dn = np.clip(255.0 / depth.max() * (depth - depth.min()), 0, 255).astype(np.uint8)
             Image.fromarray(dn).save(os.path.join(out_render_path, '%04d_depth.png' % int(img_idx)))
             Image.fromarray(img_out).convert("RGB").save(os.path.join(out_render_path, '%04d_img.png' % int(img_idx)))
+        if self.vis_geo:       # training.py:146-161: the shaded geometry view is what render_visdata returns when it is on
+            with torch.no_grad():
+                geo = torch.cat([self.model(px, None, camera_mat, world_mat, scale_mat, 'phong_renderer', add_noise=False, eval_mode=True,
+                                            it=it, depth_img=dpt, img_size=(h, w))['rgb'] for px in torch.split(pixels, 1024, dim=1)], dim=1)
+            img_out = (geo.view(h, w, 3).cpu().numpy() * 255).astype(np.uint8)
+            if out_render_path is not None:
+                from PIL import Image
+                Image.fromarray(img_out).convert("RGB").save(os.path.join(out_render_path, '%04d_geo.png' % int(img_idx)))
         return img_out

@@ -269,3 +269,97 @@ def test_render_visdata_vs_live_reference(tmp_path):
     assert img.shape == img_ref.shape == (H, W, 3) and diff <= 1, diff
     for f in ("0001_img.png", "0001_depth.png"):
         assert os.path.exists(str(tmp_path / "ours" / f)) and os.path.exists(str(tmp_path / "ref" / f)), f
+
+
+def _geo_rig(V=4, seed=31):
+    """a field whose occupancy crosses the ray-marching threshold (alpha = 0.5 <=> density logit = 0) inside the sphere"""
+    cfg = RH.load_default_cfg()
+    torch.manual_seed(seed)
+    rig = RH.RefRig(cfg, V, "cuda")
+    with torch.no_grad():
+        rig.net.fc_density.weight.mul_(10.0); rig.net.fc_density.bias.fill_(0.0)     # logit = -0.03 +- 0.04: 22 % of space occupied
+    return cfg, rig, _init_state(rig, V, 95)
+
+
+def test_infer_occ_and_gradient_vs_live_reference():
+    """OfficialStaticNerf.infer_occ / gradient (official_nerf.py:46-67: normals of the geometry view = -d logit / d p by autograd in the
+    reference, the data-gradient chain of nnb_field_bwd here)"""
+    cfg, rig, state = _geo_rig()
+    trainer, net, pose, dist, model = _ours(cfg, 4, state)
+    g = torch.Generator().manual_seed(8)
+    p = ((torch.rand(4096, 3, generator=g) - 0.5) * 6.0).cuda()
+    _, s_ref = rig.net.infer_occ(p)
+    _, s = net.infer_occ(p)
+    g_ref = rig.net.gradient(p.clone(), 0).detach()
+    g_our = net.gradient(p.clone(), 0).detach()
+    e = dict(logit=rel(s, s_ref), grad=rel(g_our, g_ref), shape=float(g_our.shape == g_ref.shape))
+    _report("infer_occ_gradient", **e)
+    assert e["shape"] == 1.0 and e["logit"] < 1e-5 and e["grad"] < 1e-4, e
+
+
+def test_phong_renderer_vs_live_reference(tmp_path):
+    """Renderer.phong_renderer (rendering.py:198-271: 512-step ray marching + 8 secant steps + normals + shading) and the geometry view
+    of Trainer.render_visdata (training.py:146-161).  A pixel whose occupancy sits at the threshold may resolve to another march step on
+    the other implementation: at most 1 % of the pixels may differ by more than 2 / 255."""
+    cfg, rig, state = _geo_rig()
+    H, W, V = 24, 32, 4
+    trainer, net, pose, dist, model = _ours(cfg, V, state)
+    data = _small_scene(H, W, V=V)
+    import model.common as mc
+    pixels = mc.arange_pixels((H, W), 1)[1].cuda()
+    cam = data["img.camera_mat"].cuda(); smat = data["img.scale_mat"].cuda()
+    def shade(mod, ps, view):
+        with torch.no_grad():
+            c2w = ps(view)
+        o = mod(pixels, None, cam, torch.inverse(c2w).unsqueeze(0), smat, "phong_renderer", it=0, eval_mode=True, depth_img=None, add_noise=False,
+                img_size=(H, W))
+        return (o["rgb"].detach().reshape(-1, 3), o["rgb_surf"].detach().reshape(-1, 3))
+    view = 1
+    for v in range(V):          # a view whose camera sits in free space and sees a surface (random field: not every pose does)
+        if float((shade(rig.model, rig.pose, v)[1].abs().sum(1) > 0).float().mean()) > 0.02:
+            view = v; break
+    outs = [shade(rig.model, rig.pose, view), shade(model, pose, view)]
+    data["img.idx"] = torch.tensor([view])
+    hit_ref = (outs[0][1].abs().sum(1) > 0)
+    bad = ((outs[0][0] - outs[1][0]).abs().max(1).values > 2.0 / 255) | ((outs[0][1] - outs[1][1]).abs().max(1).values > 2.0 / 255)
+    e = dict(frac_bad=float(bad.float().mean()), frac_surface=float(hit_ref.float().mean()),
+             med_rgb=float((outs[0][0] - outs[1][0]).abs().median()), med_surf=float((outs[0][1] - outs[1][1]).abs().median()))
+    _report("phong_renderer", **e)
+    assert 0.02 < e["frac_surface"] <= 1.0, e                  # the scene has a visible surface
+    assert e["frac_bad"] <= 0.01 and e["med_rgb"] < 1e-4 and e["med_surf"] < 1e-4, e
+    # render_visdata with vis_geo (configs/default.yaml:106): returns the shaded view and writes %04d_geo.png
+    cfg2 = RH.load_default_cfg(); assert cfg2["training"]["vis_geo"] is True
+    (tmp_path / "ref").mkdir(); (tmp_path / "ours").mkdir()
+    img_ref = rig.trainer.render_visdata(data, (H, W), 0, str(tmp_path / "ref"))
+    img = trainer.render_visdata(data, (H, W), 0, str(tmp_path / "ours"))
+    far = (np.abs(img.astype(np.int32) - img_ref.astype(np.int32)).max(-1) > 2).mean()
+    assert img.shape == img_ref.shape and far <= 0.01, far
+    assert os.path.exists(str(tmp_path / "ours" / ("%04d_geo.png" % view)))
+
+
+def test_invariant_depth_loss_vs_live_reference(monkeypatch):
+    """training.depth_loss_type = 'invariant' (losses.py:34-57): one Trainer.train_step against the live reference, small scene"""
+    from nope_nerf_b200 import ops
+    ops.set_default_engine("tc")
+    H, W, V, N, S = 48, 64, 4, 256, 64
+    cfg = RH.load_default_cfg()
+    RH.set_cfg(cfg, {"training.depth_loss_type": "invariant", "training.pc_weight": [0.0, 0.0], "training.rgb_s_weight": [0.0, 0.0],
+                     "training.n_training_points": N, "rendering.num_points": S, "training.vis_reprojection_every": 10 ** 9})
+    torch.manual_seed(77)
+    rig = RH.RefRig(cfg, V, "cuda")
+    state = _init_state(rig, V, 94)
+    data = _small_scene(H, W, V=V)
+    g = torch.Generator().manual_seed(78)
+    ray_idx = torch.randperm(H * W, generator=g)[:N].cuda(); noise = torch.rand(1, N, S, generator=g).cuda()
+    real_randperm, real_rand = torch.randperm, torch.rand
+    monkeypatch.setattr(torch, "randperm", lambda n, *a, **k: ray_idx if n == H * W else real_randperm(n, *a, **k))
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: noise if tuple(a) == (1, N, S) else real_rand(*a, **k))
+    ld_ref = rig.train_step(data)
+    gref = dict(r=rig.pose.r.grad.clone(), t=rig.pose.t.grad.clone(), shifts=rig.dist.global_shifts.grad.clone())
+    trainer, net, pose, dist, _ = _ours(cfg, V, state)
+    ld = trainer.train_step(data, it=1, epoch=0, scheduling_start=10000, render_path="/tmp")
+    e = dict(loss=abs(float(ld["loss"]) - float(ld_ref["loss"])) / abs(float(ld_ref["loss"])),
+             loss_depth=abs(float(ld["loss_depth"]) - float(ld_ref["loss_depth"])) / abs(float(ld_ref["loss_depth"])),
+             g_r=rel(pose.r.grad, gref["r"]), g_t=rel(pose.t.grad, gref["t"]), g_shifts=rel(dist.global_shifts.grad, gref["shifts"]))
+    _report("invariant_depth", **e)
+    assert e["loss"] < 1e-5 and e["loss_depth"] < 1e-5 and e["g_r"] < 2e-3 and e["g_t"] < 2e-3 and e["g_shifts"] < 2e-3, e
