@@ -522,9 +522,10 @@ class Trainer(object):
         n = L.NUM_PARAMS + 8 * V + 4
         dev = self.device
         if self._gbuf is None or self._gbuf.numel() != n:
-            if self.world > 1 and self.peer_exchange and torch.device(dev).type == 'cuda':
-                from ..peer import PeerGradExchange
-                self._peer = PeerGradExchange(n, dev, self.dp_group)
+            if self.peer_exchange and torch.device(dev).type == 'cuda' and (self.world > 1 or self.fused_adam):
+                from ..peer import PeerGradExchange, LocalGradExchange
+                # world == 1: the exchange kernel degenerates to ONE multi-tensor Adam launch over all parameter groups
+                self._peer = PeerGradExchange(n, dev, self.dp_group) if self.world > 1 else LocalGradExchange(n, dev)
                 self._gbuf = self._peer.grad
             else:
                 self._peer = None

@@ -69,3 +69,16 @@ class PeerGradExchange:
             s.p, s.m, s.v, s.offset, s.count = L.ptr(p), L.ptr(m), L.ptr(v), int(off), int(cnt)
             s.lr_dev, s.step_dev, s.beta1, s.beta2, s.eps = L.ptr(lr), L.ptr(step), float(b1), float(b2), float(eps)
         L.check(L.lib.nnb_allreduce_adam(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "nnb_allreduce_adam")
+
+
+class LocalGradExchange(PeerGradExchange):
+    """world == 1: the same kernel as the data-parallel exchange, over ONE buffer -- it then is the multi-tensor Adam of the step
+    (all parameter groups in one launch instead of five) and zeroes the gradient buffer for the next step.  No IPC, no process group."""
+
+    def __init__(self, n_floats, device):
+        assert n_floats % 4 == 0
+        self.world = 1; self.rank = 0; self.n = n_floats; self.device = device
+        self.grad = torch.zeros(n_floats, device=device)
+        self.flags = torch.zeros(L.FLAG_PAD_BYTES // 4, dtype=torch.int32, device=device)
+        self.reduced = torch.zeros(n_floats, device=device)
+        self.grad_ptrs = [self.grad.data_ptr()]; self.flag_ptrs = [self.flags.data_ptr()]

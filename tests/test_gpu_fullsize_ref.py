@@ -111,12 +111,9 @@ def _init_state(rig, V, seed):
     return rig.state()
 
 
-@pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("eng", ["tc", "simt"])
+@pytest.mark.parametrize("name,eng", [(n, "tc") for n in CASES] + [("C2_render", "simt")])   # exact-fp32 engine: one full-size case (6 ms kernels)
 def test_train_step_vs_live_reference(name, eng, monkeypatch):
     from nope_nerf_b200 import ops
-    if eng == "simt" and name != "C2_render":
-        pytest.skip("exact-fp32 engine: one full-size case is enough (6 ms kernels)")
     ops.set_default_engine(eng)
     c = CASES[name]; cfg = _cfg(c); V = c["V"]; idx = 7
     torch.manual_seed(1234)
