@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("NNB_LIB_PATH") or os.path.join(HERE, "libnope_nerf_b2
 
 NUM_PARAMS = 595844
 DIST_ALPHA, NDC, NORMALISE, USE_DIR, WHITE_BG, EVAL, SOFTPLUS, SHIFT_FIRST, STASH, TCBWD, WG16, RAW_DENSITY = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048
+FWD_DROP_WLO, FWD_DROP_ALO = 4096, 8192
 ENGINE_SIMT, ENGINE_TC = 0, 1
 
 _f = C.c_void_p  # device pointers travel as integers

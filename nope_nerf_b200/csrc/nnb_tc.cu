@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(448, 1) tc_field_fwd(nnb_render_args a, const 
       const uint32_t e_hi0 = desc_lo(smem_u32(smem + SM_EHI)), e_lo0 = desc_lo(smem_u32(smem + SM_ELO));
       const uint32_t w_lo0 = desc_lo(smem_u32(smem + SM_W));
       const uint32_t bar_full0 = BAR(B_FULL), bar_empty0 = BAR(B_EMPTY), bar_aready0 = BAR(B_AREADY);
+      const uint32_t fmode = (a.flags >> 12) & 3u;   // NNB_FWD_DROP_WLO | NNB_FWD_DROP_ALO
       int tv = 0;   // number of VALID tiles processed so far (phase bookkeeping of the per-tile barriers)
 #ifdef NNB_TC_PROFILE
       unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -227,8 +228,13 @@ __global__ void __launch_bounds__(448, 1) tc_field_fwd(nnb_render_args a, const 
               tc_fence_after();
               const uint32_t wb = w_lo0 + slot * (STAGE_BYTES >> 4);
               const uint32_t nslot = (slot + 1 == NST) ? 0u : slot + 1, nphase = (slot + 1 == NST) ? phase ^ 1u : phase;
-              if (ts) full_ok = tc_stage6<CL, true>(d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
-              else full_ok = tc_stage6<CL, false>(d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              if (fmode == 0u) {
+                if (ts) full_ok = tc_stage6<CL, true>(d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+                else full_ok = tc_stage6<CL, false>(d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              } else {   // NNB_FWD_DROP_*: fewer terms of the split (precision experiment)
+                if (ts) full_ok = tc_stage6_sel<CL, true>(fmode, d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+                else full_ok = tc_stage6_sel<CL, false>(fmode, d_tmem, aL, aH, wb, 256u, idesc, acc, bar_empty0 + 8u * slot, cmask, bar_full0 + 8u * nslot, nphase);
+              }
               acc = 1u; slot = nslot; phase = nphase;
             };
             for (int st = 0; st < e_stages; ++st) stage(false, e_lo0 + st * 512, e_hi0 + st * 512);

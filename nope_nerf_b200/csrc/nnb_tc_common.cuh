@@ -433,67 +433,85 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 
 // Two K-steps of one 128-column half against one 16 KB weight stage ([hi: K-step 0 | K-step 1][lo: K-step 0 | K-step 1], 4096 B each):
 // probe of the next stage's barrier, six MMAs, release of the stage; the second K-step's operands are +256 descriptor units (A in
 // shared memory) or +8 tensor-memory columns (A in tensor memory, TS = true).
-template <int CL, bool TS>
+// MODE (forward-precision experiment, NNB_FWD_DROP_*): 0 = the three-term split; 1 = without a_hi*b_lo (weights rounded to one fp16);
+// 2 = without a_lo*b_hi (activations rounded to one fp16); 3 = a_hi*b_hi only.  PA / PB are the predicates of the a_lo*b_hi /
+// a_hi*b_lo MMAs ("e" = the elected lane, "n" = never), ACCB / ACCC the accumulate predicates of the first a_hi*b_lo / a_hi*b_hi MMA.
+#define NNB_STAGE6_SS(PA, PB, ACCB, ACCC)                                                                                        \
+        "{\n\t.reg .pred p, q, t, e, n, ct, cm;\n\t.reg .b32 x;\n\t.reg .b64 al0, ah0, al1, ah1, bh0, bl0, bh1, bl1;\n\t"           \
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"                                                             \
+        "setp.ne.b32 p, %6, 0;\n\t"                                                                                             \
+        "setp.eq.u32 t, 0, 0;\n\t"                                                                                              \
+        "setp.ne.u32 n, 0, 0;\n\t"                                                                                              \
+        "elect.sync _|e, 0xffffffff;\n\t"                                                                                       \
+        "mov.b64 al0, {%2, %11};\n\t mov.b64 ah0, {%3, %11};\n\t"                                                               \
+        "add.u32 x, %2, 256;\n\t mov.b64 al1, {x, %11};\n\t add.u32 x, %3, 256;\n\t mov.b64 ah1, {x, %11};\n\t"                 \
+        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, %13;\n\t mov.b64 bh1, {x, %11};\n\t"                                        \
+        "add.u32 x, x, %13;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, x, %13;\n\t mov.b64 bl1, {x, %11};\n\t"                   \
+        "@" PA " tcgen05.mma.cta_group::1.kind::f16 [%1], al0, bh0, %5, p;\n\t"                                                 \
+        "@" PB " tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bl0, %5, " ACCB ";\n\t"                                          \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bh0, %5, " ACCC ";\n\t"                                               \
+        "@" PA " tcgen05.mma.cta_group::1.kind::f16 [%1], al1, bh1, %5, t;\n\t"                                                 \
+        "@" PB " tcgen05.mma.cta_group::1.kind::f16 [%1], ah1, bl1, %5, t;\n\t"                                                 \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah1, bh1, %5, t;\n\t"                                                      \
+        "setp.eq.u32 t, %12, 1;\n\t"                                                                                            \
+        "and.pred ct, e, t;\n\t"                                                                                                \
+        "not.pred t, t;\n\t"                                                                                                    \
+        "and.pred cm, e, t;\n\t"                                                                                                \
+        "@ct tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"                                   \
+        "@cm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %10;\n\t"           \
+        "selp.u32 %0, 1, 0, q;\n\t}"
+#define NNB_STAGE6_TS(PA, PB, ACCB, ACCC)                                                                                        \
+        "{\n\t.reg .pred p, q, t, e, n, ct, cm;\n\t.reg .b32 x, al1, ah1;\n\t.reg .b64 bh0, bl0, bh1, bl1;\n\t"                   \
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"                                                             \
+        "setp.ne.b32 p, %6, 0;\n\t"                                                                                             \
+        "setp.eq.u32 t, 0, 0;\n\t"                                                                                              \
+        "setp.ne.u32 n, 0, 0;\n\t"                                                                                              \
+        "elect.sync _|e, 0xffffffff;\n\t"                                                                                       \
+        "add.u32 al1, %2, 8;\n\t add.u32 ah1, %3, 8;\n\t"                                                                       \
+        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, %13;\n\t mov.b64 bh1, {x, %11};\n\t"                                        \
+        "add.u32 x, x, %13;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, x, %13;\n\t mov.b64 bl1, {x, %11};\n\t"                   \
+        "@" PA " tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], bh0, %5, p;\n\t"                                                \
+        "@" PB " tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bl0, %5, " ACCB ";\n\t"                                         \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bh0, %5, " ACCC ";\n\t"                                              \
+        "@" PA " tcgen05.mma.cta_group::1.kind::f16 [%1], [al1], bh1, %5, t;\n\t"                                               \
+        "@" PB " tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bl1, %5, t;\n\t"                                               \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bh1, %5, t;\n\t"                                                    \
+        "setp.eq.u32 t, %12, 1;\n\t"                                                                                            \
+        "and.pred ct, e, t;\n\t"                                                                                                \
+        "not.pred t, t;\n\t"                                                                                                    \
+        "and.pred cm, e, t;\n\t"                                                                                                \
+        "@ct tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"                                   \
+        "@cm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %10;\n\t"           \
+        "selp.u32 %0, 1, 0, q;\n\t}"
+#define NNB_STAGE6_OPERANDS                                                                                                      \
+        : "=r"(ok)                                                                                                              \
+        : "r"(d_tmem), "r"(aL), "r"(aH), "r"(wb), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask), \
+          "r"(DESC_HI), "r"((uint32_t)CL), "r"(b_ks)                                                                            \
+        : "memory"
+template <int CL, bool TS, int MODE = 0>
 __device__ __forceinline__ uint32_t tc_stage6(uint32_t d_tmem, uint32_t aL, uint32_t aH, uint32_t wb, uint32_t b_ks, uint32_t idesc, uint32_t acc, uint32_t empty_bar,
                                               uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
   uint32_t ok;
   if (!TS) {
-    asm volatile(
-        "{\n\t.reg .pred p, q, t, e, ct, cm;\n\t.reg .b32 x;\n\t.reg .b64 al0, ah0, al1, ah1, bh0, bl0, bh1, bl1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.eq.u32 t, 0, 0;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "mov.b64 al0, {%2, %11};\n\t mov.b64 ah0, {%3, %11};\n\t"
-        "add.u32 x, %2, 256;\n\t mov.b64 al1, {x, %11};\n\t add.u32 x, %3, 256;\n\t mov.b64 ah1, {x, %11};\n\t"
-        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, %13;\n\t mov.b64 bh1, {x, %11};\n\t"
-        "add.u32 x, x, %13;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, x, %13;\n\t mov.b64 bl1, {x, %11};\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al0, bh0, %5, p;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bl0, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah0, bh0, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al1, bh1, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah1, bl1, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah1, bh1, %5, t;\n\t"
-        "setp.eq.u32 t, %12, 1;\n\t"
-        "and.pred ct, e, t;\n\t"
-        "not.pred t, t;\n\t"
-        "and.pred cm, e, t;\n\t"
-        "@ct tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
-        "@cm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %10;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t}"
-        : "=r"(ok)
-        : "r"(d_tmem), "r"(aL), "r"(aH), "r"(wb), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask),
-          "r"(DESC_HI), "r"((uint32_t)CL), "r"(b_ks)
-        : "memory");
+    if (MODE == 0) asm volatile(NNB_STAGE6_SS("e", "e", "t", "t") NNB_STAGE6_OPERANDS);
+    else if (MODE == 1) asm volatile(NNB_STAGE6_SS("e", "n", "t", "t") NNB_STAGE6_OPERANDS);
+    else if (MODE == 2) asm volatile(NNB_STAGE6_SS("n", "e", "p", "t") NNB_STAGE6_OPERANDS);
+    else asm volatile(NNB_STAGE6_SS("n", "n", "t", "p") NNB_STAGE6_OPERANDS);
   } else {
-    asm volatile(
-        "{\n\t.reg .pred p, q, t, e, ct, cm;\n\t.reg .b32 x, al1, ah1;\n\t.reg .b64 bh0, bl0, bh1, bl1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.eq.u32 t, 0, 0;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "add.u32 al1, %2, 8;\n\t add.u32 ah1, %3, 8;\n\t"
-        "mov.b64 bh0, {%4, %11};\n\t add.u32 x, %4, %13;\n\t mov.b64 bh1, {x, %11};\n\t"
-        "add.u32 x, x, %13;\n\t mov.b64 bl0, {x, %11};\n\t add.u32 x, x, %13;\n\t mov.b64 bl1, {x, %11};\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], bh0, %5, p;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bl0, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], bh0, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [al1], bh1, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bl1, %5, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bh1, %5, t;\n\t"
-        "setp.eq.u32 t, %12, 1;\n\t"
-        "and.pred ct, e, t;\n\t"
-        "not.pred t, t;\n\t"
-        "and.pred cm, e, t;\n\t"
-        "@ct tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
-        "@cm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %10;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t}"
-        : "=r"(ok)
-        : "r"(d_tmem), "r"(aL), "r"(aH), "r"(wb), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask),
-          "r"(DESC_HI), "r"((uint32_t)CL), "r"(b_ks)
-        : "memory");
+    if (MODE == 0) asm volatile(NNB_STAGE6_TS("e", "e", "t", "t") NNB_STAGE6_OPERANDS);
+    else if (MODE == 1) asm volatile(NNB_STAGE6_TS("e", "n", "t", "t") NNB_STAGE6_OPERANDS);
+    else if (MODE == 2) asm volatile(NNB_STAGE6_TS("n", "e", "p", "t") NNB_STAGE6_OPERANDS);
+    else asm volatile(NNB_STAGE6_TS("n", "n", "t", "p") NNB_STAGE6_OPERANDS);
   }
   return ok;
+}
+// runtime selection of the split (warp-uniform mode): the default mode keeps its own straight-line copy
+template <int CL, bool TS>
+__device__ __forceinline__ uint32_t tc_stage6_sel(uint32_t mode, uint32_t d_tmem, uint32_t aL, uint32_t aH, uint32_t wb, uint32_t b_ks, uint32_t idesc, uint32_t acc,
+                                                  uint32_t empty_bar, uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
+  if (mode == 1u) return tc_stage6<CL, TS, 1>(d_tmem, aL, aH, wb, b_ks, idesc, acc, empty_bar, cmask, next_full_bar, next_parity);
+  if (mode == 2u) return tc_stage6<CL, TS, 2>(d_tmem, aL, aH, wb, b_ks, idesc, acc, empty_bar, cmask, next_full_bar, next_parity);
+  return tc_stage6<CL, TS, 3>(d_tmem, aL, aH, wb, b_ks, idesc, acc, empty_bar, cmask, next_full_bar, next_parity);
 }
 // single MMA from descriptor LOW words (high word shared), issued by the elect.sync lane of a converged warp
 __device__ __forceinline__ void tc_mma_lo_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {

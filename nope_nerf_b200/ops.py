@@ -12,6 +12,15 @@ _TC_BACKWARD = [True]     # tcgen05 backward (operand-plane stash); False -> fp3
 # 'exact' = bf16 hi|lo planes, three MMAs per product (MLP weight gradients to fp32 round-off).  NNB_WGRAD overrides.
 import os as _os
 _WGRAD = [_os.environ.get("NNB_WGRAD", "fp16")]
+# forward-precision EXPERIMENT of the tcgen05 engine (never the default): 0 = three-term split, 1 = without
+# a_hi*b_lo (NNB_FWD_DROP_WLO), 2 = without a_lo*b_hi (NNB_FWD_DROP_ALO), 3 = a_hi*b_hi only
+_FWD_DROP = [int(_os.environ.get("NNB_FWD_DROP", "0"))]
+
+
+def set_forward_split_experiment(mode):
+    if mode not in (0, 1, 2, 3):
+        raise ValueError("forward split experiment mode must be 0..3")
+    _FWD_DROP[0] = mode
 
 
 def set_wgrad_precision(mode):
@@ -132,6 +141,8 @@ class RenderCall:
             if engine == L.ENGINE_TC and _TC_BACKWARD[0]:
                 flags |= L.TCBWD
                 if (wgrad or _WGRAD[0]) == "fp16": flags |= L.WG16
+        if engine == L.ENGINE_TC and _FWD_DROP[0]:
+            flags |= (_FWD_DROP[0] & 1) * L.FWD_DROP_WLO | ((_FWD_DROP[0] >> 1) & 1) * L.FWD_DROP_ALO
         a.flags = flags; a.engine = engine
         self.rgb = torch.empty(N, 3, device=dev); self.depth_pred = torch.empty(N, device=dev)
         self.depth_gt = torch.empty(N, device=dev); self.mask = torch.empty(N, dtype=torch.uint8, device=dev)
