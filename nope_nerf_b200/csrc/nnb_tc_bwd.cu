@@ -349,6 +349,68 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
         // the A version this epilogue writes is c_pos_aver[pos] + 1: odd -> shared memory, even -> tensor memory (the MMAs of THIS
         // position read the other medium, so half 0 is converted while the tensor core still works on half 1)
         const bool next_tmem = ((c_pos_aver[pos] + 1) & 1) == 0;
+        if (gpl16) {
+          // NNB_WG16 positions that write an A version: the NEXT chunk's tcgen05.ld is issued BEFORE this chunk's plane stores.  In the
+          // plain order below the load's 32 destination registers are the stores' data / address registers (write-after-read), so
+          // every load waited until the LSU had drained the previous chunk's stores (same finding as in tc_field_fwd).
+          uint32_t r[32];
+          bool issued = false;
+          const uint32_t use0 = (uint32_t)t * 11u + (uint32_t)pos, use1 = (uint32_t)t * 9u + (uint32_t)c_pos_ord1[pos];
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            const int h = k >> 1, ci = k & 1;
+            const int cb = 4 * h + 2 * ci + half;
+            if (!issued) {
+              if (ci == 0) { mbar_wait(BAR(D_ACCFULL + h), (h ? use1 : use0) & 1u); tc_fence_after(); }
+              tc_ld32_issue(lane_addr + cb * 32, r);
+            }
+            tc_wait_ld();
+            float v[32];
+            const int mk = cb >> 1;
+            const uint32_t mw = (mk == 0) ? mq0 : (mk == 1) ? mq1 : (mk == 2) ? mq2 : mq3;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (pos == 1) x = fmaf(g_s, s_small[384 + cb * 32 + j], x);
+              v[j] = ((mw >> j) & 1u) ? x : 0.f;
+            }
+            {
+              uint32_t hw[16], lw[16];
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) split8_bf16_words(v + kb * 8, hw + kb * 4, lw + kb * 4);
+              if (next_tmem) {
+                tc_st16(lane_addr + TM_AHI + cb * 16, hw); tc_st16(lane_addr + TM_ALO + cb * 16, lw);
+                tc_wait_st();
+                tc_fence_before();
+              } else {
+                store_words_smem(hw, lw, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16);
+                fence_async_smem();
+              }
+            }
+            mbar_arrive(BAR(D_AREADY + (cb >> 1)));
+            issued = false;
+            if (ci == 0) {                                  // second chunk of the same half accumulator
+              tc_ld32_issue(lane_addr + (cb + 2) * 32, r); issued = true;
+            } else if (h == 0 && mbar_probe(BAR(D_ACCFULL + 1), use1 & 1u)) {   // half 1 usually finished under half 0's epilogue
+              tc_fence_after();
+              tc_ld32_issue(lane_addr + (4 + half) * 32, r); issued = true;
+            }
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) stream8_f16_scaled(v + kb * 8, scd, gpl16 + (cb * 4 + kb) * 1024);
+            if (k == 0) {   // max |dY_l| sample: this thread's first chunk (a quarter of the columns)
+              float mx = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+              const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+              if (lane == 0) atomicMax(&s_amax[di], mb);
+            }
+            if (ci == 1) {
+              tc_fence_before();
+              mbar_arrive(BAR(D_ACCEMPTY + h));
+            }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int h = 0; h < nhalf; ++h) {
           const uint32_t use = h ? (uint32_t)t * 9u + (uint32_t)c_pos_ord1[pos] : (uint32_t)t * 11u + (uint32_t)pos;
