@@ -418,61 +418,6 @@ __global__ void __launch_bounds__(448, 1) tc_field_fwd(nnb_render_args a, const 
             __stcs(st.mask + ((size_t)(g < 8 ? g : 8) * st.Mpad + m) * 8 + cb, mw);   // column j at bit 31 - j (epi_chunk32)
         };
         const int nhalf = (g == 9) ? 1 : 2;
-        if (planes && wg16 && dbg == 0 && g != 7 && g != 9) {
-          // Layers whose side work is only the X-plane words and the gate word (both already packed): the NEXT chunk's tcgen05.ld is
-          // issued BEFORE this chunk's global stores.  In the plain order the load sat behind them: its 32 destination registers
-          // overlap the stores' address / data registers (write-after-read on R4..R35 in the SASS), so it could not issue until the
-          // LSU had drained them -- ~500 cycles per chunk against ~140 in the inference path (NNB_TC_PROFILE counters).
-          uint32_t r[32];
-          bool issued = false;
-#pragma unroll 1
-          for (int k = 0; k < 4; ++k) {
-            const int h = k >> 1, ci = k & 1;
-            const int cb = 4 * h + 2 * ci + half;          // same chunk order as the plain loop below
-            if (!issued) {
-              if (ci == 0) {
-                const uint32_t use = h ? (uint32_t)t * 9u + (uint32_t)g : (uint32_t)t * 10u + (uint32_t)g;
-                mbar_wait(BAR(B_ACCFULL + h), use & 1u);
-                tc_fence_after();
-              }
-              tc_ld32_issue(lane_addr + cb * 32, r);
-            }
-            tc_wait_ld();
-            PROF_ADD(2);
-            float v[32];
-            uint32_t hw[16], lw[16];
-            const uint32_t mw = (g == 8) ? epi_chunk32<false>(r, bias + cb * 32, v, hw, lw, true) : epi_chunk32<true>(r, bias + cb * 32, v, hw, lw, true, true);
-            PROF_ADD(3);
-            if (next_tmem) {
-              tc_st16(lane_addr + TM_AHI + cb * 16, hw); tc_st16(lane_addr + TM_ALO + cb * 16, lw);
-              tc_wait_st();
-              tc_fence_before();
-            } else {
-              store_words_smem(hw, lw, A_hi + cb * 4 * 2048 + row * 16, A_lo + cb * 4 * 2048 + row * 16);
-              fence_async_smem();
-            }
-            PROF_ADD(4);
-            mbar_arrive(BAR(B_AREADY + (cb >> 1)));
-            PROF_ADD(5);
-            issued = false;
-            if (ci == 0) {                                  // second chunk of the same half: its accumulator is complete
-              tc_ld32_issue(lane_addr + (cb + 2) * 32, r); issued = true;
-            } else if (h == 0 && mbar_probe(BAR(B_ACCFULL + 1), ((uint32_t)t * 9u + (uint32_t)g) & 1u)) {   // half 1 usually finished under half 0's epilogue
-              tc_fence_after();
-              tc_ld32_issue(lane_addr + (4 + half) * 32, r); issued = true;
-            }
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb)
-              st_stream16(xplane + (cb * 4 + kb) * 1024, make_uint4(hw[kb * 4], hw[kb * 4 + 1], hw[kb * 4 + 2], hw[kb * 4 + 3]));
-            if (g < 8) __stcs(st.mask + ((size_t)g * st.Mpad + m) * 8 + cb, mw);
-            if (ci == 1) {
-              tc_fence_before();
-              mbar_arrive(BAR(B_ACCEMPTY + h));
-            }
-            PROF_ADD(6);
-          }
-          continue;
-        }
 #pragma unroll 1
         for (int h = 0; h < nhalf; ++h) {
           const uint32_t use = h ? (uint32_t)t * 9u + (uint32_t)g : (uint32_t)t * 10u + (uint32_t)g;
