@@ -35,7 +35,8 @@ extern "C" {
 #define NNB_TCBWD 512u      /* NNB_ENGINE_TC only: tcgen05 backward (operand-image stash) instead of the fp32 one */
 #define NNB_RAW_DENSITY 2048u /* nnb_field_fwd/bwd only: out_rgba[3] = the density LOGIT (fc_density output, official_nerf.py:66-67
                                 * infer_occ) instead of alpha / sigma; used for OfficialStaticNerf.gradient() (normals)            */
-#define NNB_FWD_DROP_WLO 4096u /* tcgen05 forward, precision experiment: skip the a_hi*b_lo MMAs (weights = one fp16) */
+#define NNB_FWD_DROP_WLO 4096u /* tcgen05 forward, precision experiment (only in a library built with
+                                  -DNNB_FWD_SPLIT_EXPERIMENT, else rc -7): skip the a_hi*b_lo MMAs (weights = one fp16) */
 #define NNB_FWD_DROP_ALO 8192u /* tcgen05 forward, precision experiment: skip the a_lo*b_hi MMAs (activations = one fp16) */
 #define NNB_WG16 1024u      /* with NNB_TCBWD: the weight-gradient GEMMs dW = dY^T X read ONE fp16 plane per operand (X = the hi
                              * half of the forward's fp16 hi|lo operand, dY = fp16 of dY * 2^k with a per-layer power-of-two scale

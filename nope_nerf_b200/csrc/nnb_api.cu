@@ -103,6 +103,10 @@ static int check_args(const nnb_render_args* a) {
 
 int nnb_render_fwd(const nnb_render_args* a, void* stream) {
   int rc = check_args(a); if (rc) return rc;
+#ifndef NNB_FWD_SPLIT_EXPERIMENT
+  if (a->flags & (NNB_FWD_DROP_WLO | NNB_FWD_DROP_ALO))
+    return fail(-7, "NNB_FWD_DROP_* needs a library built with -DNNB_FWD_SPLIT_EXPERIMENT (tools/fwd_split_check.py)");
+#endif
   WsLayout L = make_layout(a->N, a->S, a->flags, a->engine);
   cudaError_t e;
 #ifdef NNB_WITH_TC

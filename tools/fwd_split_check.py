@@ -2,7 +2,10 @@
 """Forward-precision experiment of the tcgen05 engine ("measure a 2-term MMA against the 1e-4 forward gate").
 For each split mode (0 = a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, 1 = without a_hi*b_lo, 2 = without a_lo*b_hi, 3 = a_hi*b_hi only) on the
 C2-size batch (1024 rays x 128 samples, 1080x1920): max |rgb| / |depth| error and pose / weight gradient error against the exact-fp32
-SIMT engine, and the forward / forward+backward time (CUDA events).  Needs a GPU:   python tools/fwd_split_check.py [out.json]"""
+SIMT engine, and the forward / forward+backward time (CUDA events).  The product library does not carry the experiment (its
+dispatch costs 3.8 % of the forward); build an instrumented one and point NNB_LIB_PATH at it:
+    NNB_EXTRA_NVCC_FLAGS=-DNNB_FWD_SPLIT_EXPERIMENT python nope_nerf_b200/build.py --force --out nope_nerf_b200/libnnb_split.so
+    NNB_LIB_PATH=$PWD/nope_nerf_b200/libnnb_split.so python tools/fwd_split_check.py [out.json]          (needs a GPU)"""
 import json
 import os
 import sys
