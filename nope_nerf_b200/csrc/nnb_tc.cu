@@ -112,9 +112,6 @@ __device__ __forceinline__ void row_geometry_tc(const nnb_render_args& a, size_t
 template <int CL>   // CL = thread-block cluster size (1 | 2 | 4): CTAs of a cluster share every weight stage via multicast
 __global__ void __launch_bounds__(448, 1) tc_field_fwd(nnb_render_args a, const unsigned char* __restrict__ wimg, SampleRec* __restrict__ recs,
                                                         TcStash st, size_t M, int n_tiles, int stash) {
-#ifdef NNB_ASSUME_WG16_TRAIN   // A/B experiment: how much do the other modes' code paths cost the default training mode?
-  stash = 1; st.tcb = 1; st.wg16 = 1;
-#endif
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);

@@ -136,9 +136,6 @@ __device__ unsigned long long g_dgprof[148][16];   // MMA thread of tc_dgrad: 0 
 template <bool GBF, int CL>
 __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsigned char* __restrict__ wimg, DgradPtrs P, size_t M,
                                                     int n_tiles, int write_dy) {
-#ifdef NNB_ASSUME_WG16_TRAIN
-  write_dy = 1;
-#endif
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_genc = reinterpret_cast<float*>(smem + DG_GENC);     // [64][128]
@@ -160,11 +157,7 @@ __global__ void __launch_bounds__(320, 1) tc_dgrad(nnb_render_args a, const unsi
   }
   float* s_wgscale = reinterpret_cast<float*>(smem + DG_WGS);                  // [10] power-of-two scales of the fp16 dY planes
   unsigned int* s_amax = reinterpret_cast<unsigned int*>(smem + DG_WGS + 64);   // [10] max |dY| seen by this CTA (uint bits)
-#ifdef NNB_ASSUME_WG16_TRAIN
-  const bool wg16 = true;
-#else
   const bool wg16 = P.wg_state != nullptr;
-#endif
   if (threadIdx.x < 10) { s_wgscale[threadIdx.x] = wg16 ? P.wg_state[threadIdx.x] : 1.f; s_amax[threadIdx.x] = 0u; }
   for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) s_colsum[i] = 0.f;
   for (int i = threadIdx.x; i < 640; i += blockDim.x)
