@@ -116,8 +116,6 @@ __device__ __forceinline__ unsigned long long u2_pack(uint32_t a, uint32_t b) { 
 __device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
   unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
-  unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // Epilogue of one 32-column accumulator chunk of the forward chain, in ONE pass over the registers:
 //   nx = (-bias) - acc            (packed; `nbias` holds the NEGATED biases, so nx = -(acc + bias) bit for bit)
@@ -222,10 +220,6 @@ __device__ __forceinline__ void plane_stream8_bf16(const float* v, unsigned char
   if (with_lo) st_stream16(lo_dst, make_uint4(lo[0], lo[1], lo[2], lo[3]));
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 // split 8 fp32 values into hi / lo fp16 halves (x = hi + lo to ~2^-22) and store 16 B each
 __device__ __forceinline__ void split_store8(const float* v, unsigned char* hi_dst, unsigned char* lo_dst) {
   uint32_t hi[4], lo[4];
@@ -288,23 +282,6 @@ __device__ __forceinline__ void split_stream8_bf16(const float* v, unsigned char
   st_stream16(hi_dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
   st_stream16(lo_dst, make_uint4(lo[0], lo[1], lo[2], lo[3]));
 }
-// bf16 hi/lo split stored twice: shared-memory operand image (next MMA) + streaming global copy (operand plane)
-__device__ __forceinline__ void split_store8_bf16_dual(const float* v, unsigned char* hi_s, unsigned char* lo_s, unsigned char* hi_g, unsigned char* lo_g) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const uint32_t hb = *reinterpret_cast<uint32_t*>(&hh);
-    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
-    __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
-    hi[i] = hb;
-    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
-  }
-  const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]), L = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  *reinterpret_cast<uint4*>(hi_s) = H;
-  *reinterpret_cast<uint4*>(lo_s) = L;
-  if (hi_g) { st_stream16(hi_g, H); st_stream16(lo_g, L); }
-}
 // instruction descriptor with explicit operand formats (0 = fp16, 1 = bf16) and major-ness (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t make_idesc_ex(int M, int N, int afmt, int bfmt, int amaj, int bmaj) {
   return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)amaj << 15) | ((uint32_t)bmaj << 16) |
@@ -315,12 +292,6 @@ __host__ __device__ constexpr uint32_t make_idesc_ex(int M, int N, int afmt, int
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {   // both operands MN-major
   return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // ---- thread-block clusters: weight stages are fetched from L2 once per cluster and multicast to every CTA ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -329,99 +300,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {   // arrive on `bar` in every CTA of `mask`
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-// One weight stage of the split-precision GEMM chains: probe the NEXT stage's "full" barrier, issue the three MMAs
-// (a_lo*b_hi [+ optional restart of the accumulator], a_hi*b_lo, a_hi*b_hi), commit the stage's "empty" barrier, and only
-// then read the probe's predicate -- the ~110-cycle barrier round trip hides under the MMA issue.
-template <int CL>
-__device__ __forceinline__ uint32_t tc_stage_mma3(uint32_t d_tmem, uint64_t a_lo, uint64_t a_hi, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
-                                                  uint32_t acc, uint32_t empty_bar, uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
-  uint32_t ok;
-  if (CL == 1) {
-    asm volatile(
-        "{\n\t.reg .pred p, q, t;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
-        "setp.ne.b32 p, %7, 0;\n\t"
-        "setp.eq.u32 t, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %4, %6, p;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %5, %6, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, t;\n\t"
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t}"
-        : "=r"(ok)
-        : "r"(d_tmem), "l"(a_lo), "l"(a_hi), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p, q, t;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
-        "setp.ne.b32 p, %7, 0;\n\t"
-        "setp.eq.u32 t, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %4, %6, p;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %5, %6, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, t;\n\t"
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], %11;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t}"
-        : "=r"(ok)
-        : "r"(d_tmem), "l"(a_lo), "l"(a_hi), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(cmask)
-        : "memory");
-  }
-  return ok;
-}
-// One 16 KB weight stage of the N-half pipeline = TWO K-steps of a 128-column half: probe the NEXT stage's "full" barrier, issue the
-// six MMAs (per K-step: a_lo*b_hi [+ restart], a_hi*b_lo, a_hi*b_hi), commit the stage's "empty" barrier, then read the probe.
-// TS = false: A operands are shared-memory descriptors; TS = true: A operands are TENSOR-MEMORY addresses (low 32 bits used).
-template <int CL, bool TS>
-__device__ __forceinline__ uint32_t tc_stage_mma6(uint32_t d_tmem, uint64_t a_lo0, uint64_t a_hi0, uint64_t a_lo1, uint64_t a_hi1, uint64_t b_hi0,
-                                                  uint64_t b_lo0, uint64_t b_hi1, uint64_t b_lo1, uint32_t idesc, uint32_t acc, uint32_t empty_bar,
-                                                  uint16_t cmask, uint32_t next_full_bar, uint32_t next_parity) {
-  uint32_t ok;
-  if (!TS) {
-    asm volatile(
-        "{\n\t.reg .pred p, q, t;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%13], %14;\n\t"
-        "setp.ne.b32 p, %11, 0;\n\t"
-        "setp.eq.u32 t, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %6, %10, p;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %7, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %6, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %4, %8, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %9, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %8, %10, t;\n\t"
-        "setp.eq.u32 t, %15, 1;\n\t"
-        "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
-        "@!t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], %16;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t}"
-        : "=r"(ok)
-        : "r"(d_tmem), "l"(a_lo0), "l"(a_hi0), "l"(a_lo1), "l"(a_hi1), "l"(b_hi0), "l"(b_lo0), "l"(b_hi1), "l"(b_lo1), "r"(idesc), "r"(acc),
-          "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "r"((uint32_t)CL), "h"(cmask)
-        : "memory");
-  } else {
-    const uint32_t t_lo0 = (uint32_t)a_lo0, t_hi0 = (uint32_t)a_hi0, t_lo1 = (uint32_t)a_lo1, t_hi1 = (uint32_t)a_hi1;
-    asm volatile(
-        "{\n\t.reg .pred p, q, t;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%13], %14;\n\t"
-        "setp.ne.b32 p, %11, 0;\n\t"
-        "setp.eq.u32 t, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %6, %10, p;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %7, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %6, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%4], %8, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%5], %9, %10, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%5], %8, %10, t;\n\t"
-        "setp.eq.u32 t, %15, 1;\n\t"
-        "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
-        "@!t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], %16;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t}"
-        : "=r"(ok)
-        : "r"(d_tmem), "r"(t_lo0), "r"(t_hi0), "r"(t_lo1), "r"(t_hi1), "l"(b_hi0), "l"(b_lo0), "l"(b_hi1), "l"(b_lo1), "r"(idesc), "r"(acc),
-          "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "r"((uint32_t)CL), "h"(cmask)
-        : "memory");
-  }
-  return ok;
 }
 // ---- lean issue path -------------------------------------------------------------------------------------------------
 // One thread issues every MMA of a CTA; measured (tools/micro/mma_commit.cu) it sustains one tcgen05.mma per ~64 cycles only if
