@@ -36,6 +36,20 @@ class ResidentDataset(torch.utils.data.Dataset):
         if self.load_ref_img and (self.n_views < 2 or self.random_ref < 1):
             raise ValueError("reference frames need at least two views and random_ref >= 1")
 
+    @classmethod
+    def from_reference_field(cls, field, device="cuda", pin_host=True):
+        """Resident copy of the reference's loaded scene: `field` is the `DataField` that `dataloading.get_dataloader(cfg)` returns as
+        `fields['img']` (`dataloading/dataloading.py:13-45`, `dataset.py:18-153`): `.imgs` (V,3,H,W), `.dpt_depth` (V,[1,]h_d,w_d),
+        `.K`, `.ref_img` / `.random_ref`.  Items then equal what the reference's `DataLoader(batch_size=1)` collates (same keys, shapes,
+        dtypes), minus the host->device copy per step."""
+        if getattr(field, "dpt_depth", None) is None:
+            raise ValueError("the reference field holds no DPT depth maps (use_DPT=True runs the depth network inside the step: out of scope)")
+        imgs = torch.as_tensor(field.imgs, dtype=torch.float32)
+        dpts = torch.as_tensor(field.dpt_depth, dtype=torch.float32)
+        dpts = dpts.reshape(dpts.shape[0], dpts.shape[-2], dpts.shape[-1])
+        ds = cls(imgs, dpts, field.K, device=device, load_ref_img=bool(field.ref_img), random_ref=int(field.random_ref) or 1, pin_host=pin_host)
+        return ds
+
     def __len__(self):
         return self.n_views
 

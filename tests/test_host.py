@@ -232,3 +232,41 @@ def test_refstage_device_math_on_host(name, detach, scale_pcs, shift_first, tmp_
     assert relmax(o[2:18].reshape(4, 4)[:3], gr["c2w"][:3]) < 2e-5
     assert abs(o[18] - gr["scale"]) < 2e-5 * max(abs(gr["scale"]), 1.0) and abs(o[19] - gr["shift"]) < 2e-5 * max(abs(gr["shift"]), 1.0)
     assert relmax(o[20:22], gr["kxy"]) < 5e-5, (o[20:22], gr["kxy"])          # d/d(kx, ky): what LearnFocal receives from this stage
+
+
+def test_resident_dataset_equals_reference_dataloader_items(tmp_path):
+    """SURVEY.md 8(f) rank 1 against the real thing: the UNMODIFIED reference loader (oracle/_ref: dataloading.get_dataloader -> OurDataset
+    -> DataLoader(batch_size=1), dataloading/dataloading.py:13-45,105-139) reads a fixture scene in the on-disk layout of SURVEY.md
+    appendix B; ResidentDataset.from_reference_field(fields['img']) must hand out the same items (keys, shapes, dtypes, values, reference-frame
+    choice under the same `random` state)."""
+    import random
+    import sys
+    import warnings
+    from oracle import ref_harness as RH
+    if not RH.available():
+        pytest.skip("oracle/_ref missing (tools/vendor_ref.py needs /root/reference)")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from run_ref_train import write_scene
+    from nope_nerf_b200.dataloading import ResidentDataset
+    write_scene(str(tmp_path / "data" / "Test" / "images"), V=10)
+    RH.install_stubs()
+    if RH.REF not in sys.path:
+        sys.path.insert(0, RH.REF)
+    import dataloading as dl                                      # the reference's package, unchanged
+    cfg = dl.load_config(os.path.join(RH.REF, "configs", "Test", "images.yaml"), os.path.join(RH.REF, "configs", "default.yaml"))
+    cfg["dataloading"].update(path=str(tmp_path / "data" / "Test"), n_workers=0, resize_factor=None, random_ref=2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                           # pin_memory=True without a GPU
+        loader, fields = dl.get_dataloader(cfg, mode="train", shuffle=False)
+        random.seed(11)
+        ref_items = list(loader)
+    ds = ResidentDataset.from_reference_field(fields["img"], device="cpu", pin_host=False)
+    assert len(ds) == len(ref_items) == fields["img"].N_imgs
+    random.seed(11)
+    for i, ref in enumerate(ref_items):
+        ours = ds[i]
+        assert set(ours) == set(ref), (sorted(ours), sorted(ref))
+        for k, v in ref.items():
+            o = ours[k]
+            assert tuple(o.shape) == tuple(v.shape) and o.dtype == v.dtype, (k, o.shape, v.shape, o.dtype, v.dtype)
+            assert torch.equal(o, v), k
