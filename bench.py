@@ -421,7 +421,7 @@ def reference_on_device(device, steps, warm, budget_s):
     ts = sorted(ts[warm:])
     med = ts[len(ts) // 2]
     return {"value": round(NRAYS * S / med, 1), "unit": "ray-samples/s", "sec_per_step": round(med, 4), "steps_timed": len(ts),
-            "kind": "reference", "device": device, "loss": float(ld["loss"]),
+            "kind": "reference", "device": device, "loss": float(ld["loss"].detach()),
             "sample": "unmodified reference Trainer.train_step (oracle/_ref), full 1024 rays x 128 samples per step on 1080x1920 host frames "
                       "(the reference copies the frame to the device every step), median of %d timed steps after %d warm-up" % (len(ts), warm)}
 
