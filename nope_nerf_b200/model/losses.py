@@ -17,10 +17,8 @@ class Loss(nn.Module):
     def __init__(self, cfg=None):
         super().__init__()
         self.depth_loss_type = cfg['depth_loss_type']
-        self.cfg = cfg
-        if cfg.get('with_ssim', False) or cfg.get('with_auto_mask', False):
-            raise NotImplementedError("with_ssim / with_auto_mask are off by default and not part of the hot path "
-                                      "(SURVEY.md section 2 row 7)")
+        self.cfg = cfg          # 'with_auto_mask' only feeds get_reprojection_loss / get_DPT_reprojection_loss in the reference
+                                # (losses.py:65-102), which nothing calls: like there, it has no effect on forward()
 
     def get_rgb_full_loss(self, rgb_values, rgb_gt, rgb_loss_type='l2'):     # losses.py:27-32
         d = rgb_values - rgb_gt
@@ -54,8 +52,21 @@ class Loss(nn.Module):
             raise NotImplementedError(self.cfg['match_method'])
         return ops.chamfer(Xt[0], Yt[0])
 
+    @staticmethod
+    def ssim_loss_map(x, y):                                                  # losses.py:222-252 (class SSIM)
+        """(1 - SSIM) / 2 per pixel and channel of two (B,C,H,W) images: 3x3 mean windows over the reflection-padded images,
+        C1 = 0.01^2, C2 = 0.03^2, clamped to [0, 1]"""
+        c1, c2 = 0.01 ** 2, 0.03 ** 2
+        box = lambda t: F.avg_pool2d(F.pad(t, (1, 1, 1, 1), mode='reflect'), 3, 1)
+        mx, my = box(x), box(y)
+        vx, vy, cxy = box(x * x) - mx * mx, box(y * y) - my * my, box(x * y) - mx * my
+        s = ((2 * mx * my + c1) * (2 * cxy + c2)) / ((mx * mx + my * my + c1) * (vx + vy + c2))
+        return ((1 - s) / 2).clamp(0, 1)
+
     def get_rgb_s_loss(self, rgb1, rgb2, valid_points):                       # losses.py:150-157
         diff_img = (rgb1 - rgb2).abs().clamp(0, 1)
+        if self.cfg.get('with_ssim', False):
+            diff_img = 0.15 * diff_img + 0.85 * self.ssim_loss_map(rgb1, rgb2)
         return self.mean_on_mask(diff_img, valid_points)
 
     def get_depth_consistency_loss(self, d1_proj, d2, d2_proj=None, d1=None):

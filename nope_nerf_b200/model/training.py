@@ -662,6 +662,9 @@ class Trainer(object):
                                       "(configs/default.yaml:117)")
         if self.match_method != 'dense':
             raise NotImplementedError("training.match_method=%r: only 'dense' (configs/default.yaml) is fused" % (self.match_method,))
+        if self.loss.cfg.get('with_ssim', False):
+            raise NotImplementedError("training.with_ssim=True: the SSIM term of the warped-RGB loss is available in Loss.get_rgb_s_loss for "
+                                      "direct callers but not in the fused reference-image stage (configs/default.yaml:109 is False)")
 
     # ------------------------------------------------------------------------------------
     def process_data_dict(self, data, keep_pinned=False):

@@ -270,3 +270,33 @@ def test_resident_dataset_equals_reference_dataloader_items(tmp_path):
             o = ours[k]
             assert tuple(o.shape) == tuple(v.shape) and o.dtype == v.dtype, (k, o.shape, v.shape, o.dtype, v.dtype)
             assert torch.equal(o, v), k
+
+
+@pytest.mark.parametrize("with_ssim", [False, True])
+def test_rgb_s_loss_with_ssim_vs_live_reference(with_ssim):
+    """Loss.get_rgb_s_loss (losses.py:150-157) incl. the SSIM term (class SSIM, losses.py:222-252; configs/default.yaml:109 `with_ssim`)
+    against the UNMODIFIED reference class on the CPU: value and gradient with respect to both images."""
+    from oracle import ref_harness as RH
+    if not RH.available():
+        pytest.skip("oracle/_ref missing (tools/vendor_ref.py needs /root/reference)")
+    rmdl = RH.import_reference("cpu")
+    import model.losses as ref_losses                              # the reference's module (oracle/_ref on sys.path)
+    assert os.path.abspath(ref_losses.__file__).startswith(RH.REF)
+    from nope_nerf_b200.model.losses import Loss
+    cfg = {"depth_loss_type": "l1", "with_ssim": with_ssim, "with_auto_mask": False, "match_method": "dense"}
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(1, 3, 24, 32, generator=g); b = (a + 0.1 * torch.randn(1, 3, 24, 32, generator=g)).clamp(0, 1)
+    valid = torch.rand(1, 1, 24, 32, generator=g) > 0.3
+    outs = []
+    for L_ in (ref_losses.Loss(cfg), Loss(cfg)):
+        x, y = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        v = L_.get_rgb_s_loss(x, y, valid)
+        v.backward()
+        outs.append((float(v.detach()), x.grad.clone(), y.grad.clone()))
+    (v0, gx0, gy0), (v1, gx1, gy1) = outs
+    assert abs(v0 - v1) <= 1e-6 * abs(v0), (v0, v1)
+    # fp32: the variances are differences of nearly equal means, the two implementations order the operations differently
+    assert (gx0 - gx1).abs().max() <= 2e-5 * gx0.abs().max() and (gy0 - gy1).abs().max() <= 2e-5 * gy0.abs().max()
+    if with_ssim:
+        m0 = ref_losses.compute_ssim_loss(a, b); m1 = Loss.ssim_loss_map(a, b)
+        assert m0.shape == m1.shape and (m0 - m1).abs().max() < 1e-6
