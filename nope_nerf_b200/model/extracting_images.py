@@ -36,9 +36,20 @@ class Extract_Images(object):
                               ray_idx=ray_idx, depth_map=torch.ones(1, 1, device=dev), H=h, W=w, stash=False)
         return call.rgb.view(r1 - r0, w, 3), call.depth_pred.view(r1 - r0, w)
 
+    def render_geometry(self, c2w, camera_mat, scale_mat, h, w, it=0):
+        """phong-shaded surface view (extracting_images.py:80-97): Renderer.forward(..., 'phong_renderer') over 1024-pixel chunks of
+        the frame, (h,w,3) uint8 -- the same call sequence as the geometry view of Trainer.render_visdata"""
+        from .common import arange_pixels
+        dev = self.device
+        _, pixels = arange_pixels(resolution=(h, w), device=dev)
+        world_mat = torch.linalg.inv(c2w.detach().reshape(4, 4).float()).unsqueeze(0)
+        cam = camera_mat.detach().reshape(1, 4, 4).float()
+        with torch.no_grad():
+            rgb = torch.cat([self.renderer(px, None, cam, world_mat, scale_mat, 'phong_renderer', eval_=True, it=it, add_noise=False)['rgb']
+                             for px in torch.split(pixels, 1024, dim=1)], dim=1)
+        return (rgb.reshape(h, w, 3).cpu().numpy() * 255).astype(np.uint8)
+
     def generate_images(self, data, render_dir, c2ws, fxfy, it, output_geo):
-        if output_geo:
-            raise NotImplementedError("geometry (phong) output is outside the hot path (SURVEY.md 8(f) rank 4)")
         self.renderer.eval()
         device = self.device
         camera_mat = data.get('img.camera_mat').to(device)
@@ -60,4 +71,12 @@ class Extract_Images(object):
             Image.fromarray(img_out).save(os.path.join(img_dir, str(img_idx).zfill(4) + '.png'))
             Image.fromarray(d8).save(os.path.join(dep_dir, str(img_idx).zfill(4) + '.png'))
             depth_out = d8
-        return {'img': img_out, 'depth': depth_out, 'geo': None}
+        geo_out = None
+        if output_geo:
+            scale_mat = data.get('img.scale_mat')
+            geo_out = self.render_geometry(c2w, camera_mat, scale_mat.to(device) if scale_mat is not None else None, h, w, it=it)
+            if render_dir is not None:
+                from PIL import Image
+                geo_dir = os.path.join(render_dir, 'geo_out'); os.makedirs(geo_dir, exist_ok=True)
+                Image.fromarray(geo_out).save(os.path.join(geo_dir, str(img_idx).zfill(4) + '.png'))
+        return {'img': img_out, 'depth': depth_out, 'geo': geo_out}
